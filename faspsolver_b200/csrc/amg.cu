@@ -1,0 +1,426 @@
+// amg.cu — AMG hierarchy upload and the multigrid cycle on the device.
+//
+// Replaces, on the solve path:
+//   fasp_solver_mgcycle      PreMGCycle.c:48-274   (V / W / VW / WV, non-recursive)
+//   fasp_dcsr_presmoothing / _postsmoothing  PreMGSmoother.inl:49,155 (Jacobi, L1, poly)
+//   fasp_coarse_itsolver     PreMGUtil.inl:37      (-> dense inverse, dense.cu)
+//   fasp_precond_amg         PreCSR.c:416-435
+// The hierarchy itself (A_l, P_l, R_l = P_l^T) comes from FASP's host setup and is uploaded
+// once; nothing here allocates per cycle (the CPU smoothers calloc two N-vectors per call).
+//
+// Per level of a V(1,1) cycle the device runs, with x_l = 0 on entry (PreCSR.c:430,
+// PreMGCycle.c:151):
+//   pre-smooth   x = D~^-1 b              vector kernel, no pass over A (b - A*0 == b exactly)
+//   residual     w = b - A x              1 pass over A_l
+//   restrict     b_{l+1} = R w            1 pass over R_l
+//   ...coarse...
+//   prolongate   x += P x_{l+1}           1 pass over P_l
+//   post-smooth  x = S(x)                 1 pass over A_l
+#include "amg.cuh"
+
+namespace fc {
+
+static bool smoother_supported(short s)
+{
+    return s == SMOOTHER_JACOBI || s == SMOOTHER_L1DIAG || s == SMOOTHER_POLY;
+}
+
+void amg_set_params(Amg& h, const AMG_param* p)
+{
+    h.amg_type       = p->AMG_type;
+    h.smoother       = p->smoother;
+    h.cycle_type     = p->cycle_type;
+    h.presmooth      = p->presmooth_iter;
+    h.postsmooth     = p->postsmooth_iter;
+    h.ndeg           = p->polynomial_degree;
+    h.coarse_scaling = p->coarse_scaling;
+    h.coarse_solver  = p->coarse_solver;
+    h.smooth_order   = p->smooth_order;
+    h.relax          = p->relaxation;
+    h.tol            = p->tol;
+    h.maxit          = p->maxit;
+}
+
+static void level_smoother_data(Amg& h, Level& L)
+{
+    switch (h.smoother) {
+        case SMOOTHER_JACOBI: csr_ensure_diag(L.A); break;
+        case SMOOTHER_L1DIAG: csr_ensure_l1(L.A); break;
+        case SMOOTHER_POLY: {
+            // constants of fasp_smoother_dcsr_poly, ItrSmootherCSRpoly.c:94-107
+            double mu0        = 1.0 / csr_dinv_a_norminf(L.A);
+            const double mu1  = 4.0 * mu0;
+            const double smu0 = sqrt(mu0), smu1 = sqrt(mu1);
+            L.pk[1] = (mu0 + mu1) / 2.0;
+            L.pk[2] = (smu0 + smu1) * (smu0 + smu1) / 2.0;
+            L.pk[3] = mu0 * mu1;
+            L.pk[4] = 2.0 * L.pk[3] / L.pk[2];
+            L.pk[5] = (mu1 - 2.0 * smu0 * smu1 + mu0) / (mu1 + 2.0 * smu0 * smu1 + mu0);
+            for (int i = 0; i < 3; ++i)
+                if (!L.pv[i]) {
+                    L.pv[i] = dalloc<double>(L.n);
+                    h.bytes += sizeof(double) * (size_t)L.n;
+                }
+            break;
+        }
+        default: break;
+    }
+}
+
+Amg* amg_upload(AMG_data* mgl, AMG_param* param)
+{
+    ensure_init();
+    if (mgl == nullptr || param == nullptr) fail(ERROR_INPUT_PAR, "amg_upload: null argument");
+    const int nl = mgl[0].num_levels;
+    if (nl < 1 || nl > MAX_AMG_LVL) fail(ERROR_DATA_STRUCTURE, "amg_upload: num_levels = %d", nl);
+    if (mgl[0].ILU_levels > 0 || mgl[0].SWZ_levels > 0)
+        fail(ERROR_AMG_SMOOTH_TYPE, "ILU / Schwarz smoothing levels are not on the device path");
+    if (param->cycle_type == AMLI_CYCLE || param->cycle_type == NL_AMLI_CYCLE)
+        fail(ERROR_INPUT_PAR, "AMLI cycles are not on the device path (cycle_type %d)",
+             (int)param->cycle_type);
+    if (nl > 1 && !smoother_supported(param->smoother))
+        fail(ERROR_AMG_SMOOTH_TYPE,
+             "smoother %d has no data-parallel device form (supported: Jacobi 1, poly 9, L1 10)",
+             (int)param->smoother);
+
+    Amg* h = new Amg();
+    try {
+        amg_set_params(*h, param);
+        h->nl = nl;
+        h->lv.resize(nl);
+        const bool ua = (param->AMG_type == UA_AMG);
+        for (int l = 0; l < nl; ++l) {
+            Level&         L = h->lv[l];
+            const dCSRmat& A = mgl[l].A;
+            csr_upload(L.A, A.row, A.col, A.nnz, A.IA, A.JA, A.val);
+            L.n = A.row;
+            if (l < nl - 1) {
+                const dCSRmat& P = mgl[l].P;
+                const dCSRmat& R = mgl[l].R;
+                csr_upload(L.P, P.row, P.col, P.nnz, P.IA, P.JA, P.val, ua);
+                csr_upload(L.R, R.row, R.col, R.nnz, R.IA, R.JA, R.val, ua);
+                level_smoother_data(*h, L);
+            }
+            L.b  = dalloc<double>(L.n);
+            L.xa = dalloc<double>(L.n);
+            L.xb = dalloc<double>(L.n);
+            L.w  = dalloc<double>(L.n);
+            h->bytes += L.A.bytes + L.P.bytes + L.R.bytes + 4 * sizeof(double) * (size_t)L.n;
+        }
+        h->scal = dalloc<double>(4);
+        FC_CUDA(cudaMemsetAsync(h->scal, 0, 4 * sizeof(double), ctx().stream));
+        // coarsest level
+        Level& C = h->lv[nl - 1];
+        if (ctx().opt.coarse_dense && C.n <= ctx().opt.coarse_dense_max) {
+            dense_invert_csr(h->coarse, C.A);
+            h->bytes += sizeof(double) * (size_t)C.n * C.n;
+        } else {
+            fail(ERROR_AMG_SETUP,
+                 "coarsest level has %d rows > coarse_dense_max = %d: raise the option or let the "
+                 "host setup coarsen further",
+                 C.n, ctx().opt.coarse_dense_max);
+        }
+        FC_CUDA(cudaStreamSynchronize(ctx().stream));
+    } catch (...) {
+        amg_free(h);
+        throw;
+    }
+    return h;
+}
+
+void amg_free(Amg* h)
+{
+    if (!h) return;
+    for (Level& L : h->lv) {
+        csr_free(L.A);
+        csr_free(L.P);
+        csr_free(L.R);
+        dfree(L.b);
+        dfree(L.xa);
+        dfree(L.xb);
+        dfree(L.w);
+        for (int i = 0; i < 3; ++i) dfree(L.pv[i]);
+        dfree(L.color_rows);
+    }
+    dense_free(h->coarse);
+    dfree(h->scal);
+    delete h;
+}
+
+// ------------------------------------------------------------------------------------
+// smoothing
+// ------------------------------------------------------------------------------------
+namespace {
+
+struct CycleState {
+    Amg&          h;
+    const int*    done;
+    const double* b0;       // level-0 right-hand side
+    double*       x_out;    // where the final level-0 iterate must land
+    Reduce        red;      // fused into the last kernel writing x_out when possible
+    bool          red_done = false;
+    std::vector<double*> cur;     // current iterate buffer per level
+    std::vector<bool>    xzero;   // iterate known to be identically zero
+    CycleState(Amg& h_, const int* d) : h(h_), done(d), cur(h_.nl), xzero(h_.nl, false) {}
+    const double* rhs(int l) const { return l == 0 ? b0 : h.lv[l].b; }
+    double*       other(int l) const
+    {
+        Level& L = h.lv[l];
+        return cur[l] == L.xa ? L.xb : L.xa;
+    }
+};
+
+// nsweeps of the configured smoother on level l. `last` marks the final operation of the
+// whole cycle: its output goes to x_out and carries the fused reduction.
+void smooth(CycleState& s, int l, int nsweeps, bool last)
+{
+    Amg&          h = s.h;
+    Level&        L = h.lv[l];
+    const double* b = s.rhs(l);
+    const size_t  n = L.n;
+    for (int sw = 0; sw < nsweeps; ++sw) {
+        const bool final_sweep = last && sw == nsweeps - 1;
+        switch (h.smoother) {
+            case SMOOTHER_JACOBI:
+            case SMOOTHER_L1DIAG: {
+                const bool jac = (h.smoother == SMOOTHER_JACOBI);
+                double*    out = final_sweep ? s.x_out : s.other(l);
+                Reduce     red = final_sweep ? s.red : Reduce();
+                if (s.xzero[l] && ctx().opt.zero_guess) {
+                    vec_scale_div(out, jac ? h.relax : 1.0, b, jac ? L.A.diag : L.A.l1, n, red,
+                                  s.done);
+                } else {
+                    if (s.xzero[l]) vec_set(s.cur[l], 0.0, n, s.done);
+                    CsrArgs a;
+                    a.mode  = jac ? CSR_JACOBI : CSR_L1;
+                    a.alpha = h.relax;
+                    a.x     = s.cur[l];
+                    a.b     = b;
+                    a.y     = out;
+                    a.red   = red;
+                    a.done  = s.done;
+                    csr_launch(L.A, a);
+                }
+                if (final_sweep) s.red_done = true;
+                s.cur[l]   = out;
+                s.xzero[l] = false;
+                break;
+            }
+            case SMOOTHER_POLY: {
+                // fasp_smoother_dcsr_poly, ItrSmootherCSRpoly.c:114-125 + Rr :551-609
+                double*       u    = s.cur[l];
+                const double* r    = L.w;
+                double*       rbar = L.pv[0];
+                if (s.xzero[l]) {
+                    vec_set(u, 0.0, n, s.done);
+                    if (ctx().opt.zero_guess) {
+                        r = b;   // b - A*0
+                        vec_mul(rbar, L.A.dinv, b, n, s.done);
+                    }
+                }
+                if (r == L.w) {
+                    CsrArgs a;
+                    a.mode   = CSR_RESID_DINV;
+                    a.x      = u;
+                    a.b      = b;
+                    a.y      = L.w;
+                    a.v0_out = rbar;
+                    a.done   = s.done;
+                    csr_launch(L.A, a);
+                }
+                double* v0 = L.pv[1];
+                double* v1 = L.pv[2];
+                {
+                    CsrArgs a;
+                    a.mode   = CSR_POLY1;
+                    a.x      = rbar;
+                    a.y      = v1;
+                    a.v0_out = v0;
+                    a.k1 = L.pk[1], a.k2 = L.pk[2], a.k3 = L.pk[3];
+                    a.done = s.done;
+                    csr_launch(L.A, a);
+                }
+                double* vn = rbar;   // rbar is dead after POLY1
+                for (int j = 1; j < h.ndeg; ++j) {
+                    CsrArgs a;
+                    a.mode  = CSR_POLYJ;
+                    a.x     = v1;
+                    a.v0    = v0;
+                    a.b     = r;
+                    a.y     = vn;
+                    a.k4 = L.pk[4], a.k5 = L.pk[5];
+                    a.u_acc = (j == h.ndeg - 1) ? u : nullptr;   // u += error (:125)
+                    a.done  = s.done;
+                    csr_launch(L.A, a);
+                    double* t = v0;
+                    v0        = v1;
+                    v1        = vn;
+                    vn        = t;
+                }
+                s.xzero[l] = false;
+                break;
+            }
+            default: fail(ERROR_AMG_SMOOTH_TYPE, "smoother %d not on the device path", (int)h.smoother);
+        }
+    }
+}
+
+void coarse_solve(CycleState& s, bool last)
+{
+    Amg& h      = s.h;
+    const int l = h.nl - 1;
+    double* out = last ? s.x_out : s.cur[l];
+    dense_apply(h.coarse, s.rhs(l), out, s.done);
+    s.cur[l]   = out;
+    s.xzero[l] = false;
+}
+
+// the cycle of PreMGCycle.c:95-269; level-0 iterate starts in s.cur[0]
+void run_cycle(CycleState& s)
+{
+    Amg&      h  = s.h;
+    const int nl = h.nl;
+    int       num_lvl[MAX_AMG_LVL] = {0};
+    int       ncycles[MAX_AMG_LVL];
+    for (int i = 0; i < MAX_AMG_LVL; ++i) ncycles[i] = 1;
+    switch (h.cycle_type) {
+        case VW_CYCLE:
+            for (int i = MAX_AMG_LVL - 2; i > 0; i -= 2) ncycles[i] = 2;
+            break;
+        case WV_CYCLE:
+            for (int i = MAX_AMG_LVL - 1; i > 0; i -= 2) ncycles[i] = 2;
+            break;
+        default:
+            for (int i = 0; i < MAX_AMG_LVL; ++i) ncycles[i] = h.cycle_type;
+    }
+
+    int l = 0;
+    if (nl == 1) coarse_solve(s, true);
+    while (nl > 1) {
+        // ForwardSweep
+        while (l < nl - 1) {
+            Level& L = h.lv[l];
+            num_lvl[l]++;
+            smooth(s, l, h.presmooth, false);
+            if (s.xzero[l]) {   // no pre-smoothing at all: x is still zero, residual = b
+                vec_set(s.cur[l], 0.0, L.n, s.done);
+                s.xzero[l] = false;
+            }
+            CsrArgs a;   // w = b - A x   (copy + aAxpy(-1), PreMGCycle.c:136-137)
+            a.mode = CSR_RESID;
+            a.x    = s.cur[l];
+            a.b    = s.rhs(l);
+            a.y    = L.w;
+            a.done = s.done;
+            csr_launch(L.A, a);
+            CsrArgs r;   // b_{l+1} = R w  (:140-147; pattern-only for UA)
+            r.mode = CSR_MXV;
+            r.x    = L.w;
+            r.y    = h.lv[l + 1].b;
+            r.done = s.done;
+            csr_launch(L.R, r);
+            ++l;
+            s.cur[l]   = h.lv[l].xa;
+            s.xzero[l] = true;   // fasp_dvec_set(..., 0.0) (:151) is folded into the next writer
+        }
+
+        coarse_solve(s, false);
+
+        // BackwardSweep
+        while (l > 0) {
+            --l;
+            Level& L  = h.lv[l];
+            Level& Lc = h.lv[l + 1];
+            CsrArgs p;   // x_l += alpha P x_{l+1}   (:219-227)
+            p.mode = CSR_AXPY;
+            p.x    = s.cur[l + 1];
+            p.y    = s.cur[l];
+            p.done = s.done;
+            if (h.coarse_scaling == ON) {   // (:210-216)
+                vec_dot(s.cur[l + 1], Lc.b, Lc.n, h.scal + 1, s.done);
+                CsrArgs v;
+                v.mode         = CSR_MXV;
+                v.x            = s.cur[l + 1];
+                v.y            = Lc.w;
+                v.red.dot_with = s.cur[l + 1];
+                v.red.dot_out  = h.scal + 2;
+                v.done         = s.done;
+                csr_launch(Lc.A, v);
+                scaling_alpha(h.scal, s.done);
+                p.alpha_dev = h.scal;
+            }
+            csr_launch(L.P, p);
+            // the cycle ends when the backward sweep reaches level 0
+            const bool last_level_visit = (l == 0);
+            smooth(s, l, h.postsmooth, last_level_visit);
+            if (num_lvl[l] < ncycles[l]) break;
+            num_lvl[l] = 0;
+        }
+        if (l == 0) break;
+    }
+
+    // result placement + reduction when the last kernel could not do it
+    if (s.cur[0] != s.x_out) {
+        vec_copy(s.x_out, s.cur[0], h.lv[0].n, s.done);
+        s.cur[0] = s.x_out;
+    }
+    if (!s.red_done) vec_reduce(s.x_out, h.lv[0].n, s.red, s.done);
+}
+
+} // namespace
+
+// nsweeps of the level-0 smoother on (b, u), u in/out: the host-pointer smoother drop-ins
+void amg_smooth_only(Amg& h, const double* b, double* u, int nsweeps)
+{
+    CycleState s(h, nullptr);
+    s.b0       = b;
+    s.x_out    = u;
+    s.cur[0]   = u;
+    s.xzero[0] = false;
+    smooth(s, 0, nsweeps, false);
+    if (s.cur[0] != u) vec_copy(u, s.cur[0], h.lv[0].n, nullptr);
+}
+
+void amg_apply(Amg& h, const double* r, double* z, const Reduce& red, const int* done)
+{
+    CycleState s(h, done);
+    s.b0    = r;
+    s.x_out = z;
+    const int ncyc = h.maxit < 1 ? 1 : h.maxit;
+    for (int c = 0; c < ncyc; ++c) {
+        s.red      = (c == ncyc - 1) ? red : Reduce();
+        s.red_done = false;
+        if (c == 0) {
+            s.cur[0]   = h.lv[0].xa;
+            s.xzero[0] = true;
+            if (h.nl == 1) s.xzero[0] = false;
+        } else {
+            // continue from the previous cycle's iterate, which sits in z: move it to a
+            // work buffer so the final sweep can write z without aliasing its own input
+            vec_copy(h.lv[0].xa, z, h.lv[0].n, done);
+            s.cur[0]   = h.lv[0].xa;
+            s.xzero[0] = false;
+        }
+        run_cycle(s);
+    }
+}
+
+void amg_cycle_inplace(Amg& h, const double* b, double* x, bool x_is_zero, const Reduce& red,
+                       const int* done)
+{
+    CycleState s(h, done);
+    s.b0    = b;
+    s.x_out = x;
+    s.red   = red;
+    if (x_is_zero) {
+        s.cur[0]   = h.lv[0].xa;
+        s.xzero[0] = (h.nl > 1);
+    } else {
+        vec_copy(h.lv[0].xa, x, h.lv[0].n, done);
+        s.cur[0]   = h.lv[0].xa;
+        s.xzero[0] = false;
+    }
+    run_cycle(s);
+}
+
+} // namespace fc

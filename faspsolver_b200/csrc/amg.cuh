@@ -1,0 +1,63 @@
+// amg.cuh — device-resident AMG hierarchy and multigrid cycle (CSR and BSR).
+#pragma once
+#include "common.cuh"
+
+namespace fc {
+
+// dense coarsest-level operator: x = Ainv * b
+struct DenseInv {
+    int     n    = 0;
+    double* ainv = nullptr;   // n x n row-major
+};
+void dense_invert_csr(DenseInv& D, const DevCSR& A);       // Gauss-Jordan, partial pivoting
+void dense_invert_host(DenseInv& D, int n, const std::vector<double>& a_rowmajor);
+void dense_apply(const DenseInv& D, const double* b, double* x, const int* done);
+void dense_free(DenseInv& D);
+
+struct Level {
+    DevCSR  A, P, R;          // P: level l <- l+1 ; R: level l+1 <- l   (R = P^T stored explicitly)
+    int     n  = 0;
+    double* b  = nullptr;     // right-hand side on this level (level 0: caller's r)
+    double* xa = nullptr;     // iterate ping-pong buffers
+    double* xb = nullptr;
+    double* w  = nullptr;     // residual / scratch
+    // polynomial smoother (ItrSmootherCSRpoly.c:94-107)
+    double  pk[6] = {0, 0, 0, 0, 0, 0};
+    double* pv[3] = {nullptr, nullptr, nullptr};   // rbar/v0, v1, vnew rotation
+    // multicolour Gauss-Seidel (BlaSparseCSR.c:1687,2123)
+    int  ncolors = 0;
+    int* color_rows = nullptr;       // rows grouped by colour
+    std::vector<int> color_ptr;      // host offsets into color_rows
+};
+
+struct Amg {
+    std::vector<Level> lv;
+    int    nl = 0;
+    // parameters (AMG_param / precond_data members used by the cycle, PreMGCycle.c:50-59)
+    short  amg_type = CLASSIC_AMG, smoother = SMOOTHER_GS, cycle_type = V_CYCLE;
+    short  presmooth = 1, postsmooth = 1, ndeg = 3, coarse_scaling = OFF, coarse_solver = 0;
+    short  smooth_order = CF_ORDER;
+    double relax = 1.0, tol = 1e-6;
+    int    maxit = 1;             // cycles per preconditioner application (PreCSR.c:432)
+    DenseInv coarse;
+    double*  scal = nullptr;      // device scalars: [0] alpha (coarse scaling), [1],[2] dots
+    size_t   bytes = 0;
+    long long kernels_per_cycle = 0;
+};
+
+// Build from a host hierarchy produced by FASP's setup (fasp.h:804-888).
+Amg* amg_upload(AMG_data* mgl, AMG_param* param);
+void amg_free(Amg* h);
+void amg_set_params(Amg& h, const AMG_param* param);
+
+// One preconditioner application z = B r: x0 = 0, h.maxit cycles (PreCSR.c:416-435 +
+// PreMGCycle.c:48-274). r is used in place as the level-0 right-hand side; the result is
+// written to z. `red` (optional) is fused into the last kernel that writes z.
+void amg_apply(Amg& h, const double* r, double* z, const Reduce& red, const int* done);
+
+// One cycle on explicit level-0 vectors with a non-zero initial guess in x (in/out):
+// used by fasp_cuda_solver_mgcycle and the AMG-as-solver loop (PreMGSolve.c:49).
+void amg_cycle_inplace(Amg& h, const double* b, double* x, bool x_is_zero, const Reduce& red,
+                       const int* done);
+
+} // namespace fc

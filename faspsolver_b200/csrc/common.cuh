@@ -1,0 +1,263 @@
+// common.cuh — shared declarations of libfasp_cuda (B200 / sm_100a).
+//
+// Conventions
+//  * everything lives in namespace fc; only capi.cu defines extern "C" symbols
+//  * internal code throws fc::Error; the C-ABI wrappers translate to FASP status codes
+//  * all kernels are launched on ctx().stream through FC_LAUNCH so that the library can
+//    report how many of its own kernels ran (bench.py "gpu_launches")
+//  * every kernel that is part of a Krylov iteration takes `const int* done` and returns
+//    immediately when *done != 0: the host enqueues iterations ahead of the convergence
+//    test, so there is no host round-trip per iteration
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+#include "fasp_cuda.h"
+
+namespace fc {
+
+// ------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------
+struct Error {
+    int         code;
+    std::string msg;
+};
+void        set_last_error(const std::string& s);
+const char* last_error();
+
+[[noreturn]] void fail(int code, const char* fmt, ...);
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line)
+{
+    if (e == cudaSuccess) return;
+    int code = (e == cudaErrorMemoryAllocation) ? ERROR_ALLOC_MEM : ERROR_SOLVER_MISC;
+    cudaGetLastError(); // clear sticky-less error state
+    fail(code, "CUDA error %s (%s) at %s:%d: %s", cudaGetErrorName(e), what, file, line,
+         cudaGetErrorString(e));
+}
+#define FC_CUDA(call) ::fc::cuda_check((call), #call, __FILE__, __LINE__)
+
+// ------------------------------------------------------------------------------------
+// process-wide context (one process per GPU)
+// ------------------------------------------------------------------------------------
+struct Options {
+    int    strict           = 0;
+    int    coarse_dense     = 1;
+    int    coarse_dense_max = 8192;
+    int    graph            = 1;
+    int    zero_guess       = 1;
+    int    lookahead        = 2;   // Krylov iterations enqueued ahead of the status read
+};
+
+struct Ctx {
+    bool         inited   = false;
+    int          device   = 0;
+    int          sm_count = 148;
+    size_t       l2_bytes = 126u << 20;
+    cudaStream_t stream   = nullptr;
+    long long    launches = 0;
+    bool         capturing = false;     // inside a stream capture: launches counted per replay
+    long long    captured  = 0;
+    Options      opt;
+    // scratch for grid reductions (partials + ticket), grown on demand
+    double*       red_partials = nullptr;
+    size_t        red_cap      = 0;
+    unsigned int* red_ticket   = nullptr;
+    // L2 flush buffer for timing helpers
+    char*  flush_buf   = nullptr;
+    size_t flush_bytes = 0;
+};
+Ctx& ctx();
+void ensure_init();
+
+#define FC_LAUNCH(kernel, grid, block, smem, ...)                                          \
+    do {                                                                                   \
+        ::fc::Ctx& c__ = ::fc::ctx();                                                      \
+        kernel<<<(grid), (block), (smem), c__.stream>>>(__VA_ARGS__);                      \
+        if (c__.capturing) c__.captured++; else c__.launches++;                            \
+        FC_CUDA(cudaPeekAtLastError());                                                    \
+    } while (0)
+
+// device allocation helpers (throw ERROR_ALLOC_MEM)
+void* dmalloc(size_t bytes);
+void  dfree(void* p);
+template <class T> T* dalloc(size_t n) { return static_cast<T*>(dmalloc(n * sizeof(T))); }
+
+// ------------------------------------------------------------------------------------
+// device CSR matrix
+// ------------------------------------------------------------------------------------
+// HBM layout:
+//   ia     int32[rows+1]          row offsets (matrices with nnz >= 2^31 use ia64)
+//   ja     int32[nnz_pad]         column ids, padded by 8 entries so vector loads may overrun
+//   val    f64  [nnz_pad]         entries (nullptr for pattern-only operators: all ones)
+//   rowblk int32[nblk+1]          first row of every row block; a block is a run of rows
+//                                 with <= blk_cap nonzeros and <= 256 rows, or one long row
+//   diag   f64[rows], dpos int32[rows]   diagonal entry and its offset in the row (Jacobi)
+//   l1     f64[rows]              sum_k |a_ik| in storage order (L1 smoother)
+struct DevCSR {
+    int       rows = 0, cols = 0;
+    long long nnz  = 0;
+    int*      ia   = nullptr;
+    int*      ja   = nullptr;
+    double*   val  = nullptr;
+    int*      rowblk  = nullptr;
+    int       nblk    = 0;
+    int       blk_cap = 0;        // shared-memory products per CTA (entries)
+    double*   diag = nullptr;
+    int*      dpos = nullptr;
+    double*   l1   = nullptr;
+    double*   dinv = nullptr;     // 1/diag (first stored diagonal entry), poly smoother
+    size_t    bytes = 0;
+    bool      dup_diag = false;   // some row stores more than one (i,i) entry
+};
+
+// Upload a host CSR (FASP layout). `pattern_only` drops the values (UA-AMG P/R: all ones).
+void csr_upload(DevCSR& d, int rows, int cols, long long nnz, const int* ia, const int* ja,
+                const double* val, bool pattern_only = false);
+void csr_free(DevCSR& d);
+// lazily built smoother side data
+void csr_ensure_diag(DevCSR& d);   // diag + dpos (+ dup_diag)
+void csr_ensure_l1(DevCSR& d);
+void csr_ensure_dinv(DevCSR& d);
+double csr_dinv_a_norminf(DevCSR& d);   // || D^-1 A ||_inf (ItrSmootherCSRpoly.c:428)
+
+// algorithmic bytes of one pass over the matrix (SURVEY.md §8d bytes model)
+inline double csr_spmv_bytes(const DevCSR& d, bool read_y)
+{
+    double per_nnz = d.val ? 12.0 : 4.0;
+    return per_nnz * (double)d.nnz + 4.0 * (d.rows + 1) + 8.0 * d.cols + 8.0 * d.rows +
+           (read_y ? 8.0 * d.rows : 0.0);
+}
+
+// ------------------------------------------------------------------------------------
+// fused reduction targets
+// ------------------------------------------------------------------------------------
+// A kernel epilogue can accumulate up to two sums over the rows it produces; the last CTA
+// to finish adds the per-CTA partials in CTA order (deterministic) and stores the totals.
+struct Reduce {
+    const double* dot_with = nullptr;  // sum out_i * dot_with[i]
+    double*       dot_out  = nullptr;  // device scalar
+    double*       nrm2_out = nullptr;  // device scalar: sum out_i^2  (not square-rooted)
+};
+
+// ------------------------------------------------------------------------------------
+// CSR row kernels (spmv.cu)
+// ------------------------------------------------------------------------------------
+enum CsrMode {
+    CSR_MXV = 0,     // y = A x
+    CSR_AXPY = 1,    // y = y + alpha A x
+    CSR_RESID = 2,   // y = b - A x
+    CSR_JACOBI = 3,  // y = (1-w) x + w (b - sum_{j!=i} a_ij x_j)/a_ii
+    CSR_L1 = 4,      // y = x + (b - A x)/l1
+    CSR_POLY1 = 5,   // poly smoother first step  (see spmv.cu)
+    CSR_POLYJ = 6,   // poly smoother recurrence step
+    CSR_RESID_DINV = 7  // y = b - A x ; aux_out = dinv .* y   (poly smoother residual)
+};
+
+struct CsrArgs {
+    int           mode  = CSR_MXV;
+    double        alpha = 1.0;      // AXPY alpha / Jacobi weight
+    const double* alpha_dev = nullptr;  // AXPY: alpha read from the device when set
+    const double* x     = nullptr;  // gathered vector
+    const double* b     = nullptr;  // rhs (RESID/JACOBI/L1/POLY*: r)
+    double*       y     = nullptr;  // output
+    // polynomial smoother extras
+    const double* v0 = nullptr;     // POLYJ: v_{j-1}
+    double*       v0_out = nullptr; // POLY1: v0 out ; POLYJ: new v0 (= old v1)
+    double*       u_acc  = nullptr; // POLYJ (last step): u += vnew
+    double        k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0;
+    Reduce        red;
+    const int*    done = nullptr;
+};
+void csr_launch(const DevCSR& A, const CsrArgs& a);
+
+// ------------------------------------------------------------------------------------
+// BLAS-1 (blas1.cu) — all on device scalars, all early-exit on *done
+// ------------------------------------------------------------------------------------
+void vec_set(double* x, double v, size_t n, const int* done = nullptr);
+void vec_copy(double* y, const double* x, size_t n, const int* done = nullptr);
+// y = a*x + b*y with host scalars (FASP fasp_blas_darray_axpby, BlaArray.c:620)
+void vec_axpby(double a, const double* x, double b, double* y, size_t n,
+               const int* done = nullptr);
+// y = s .* x / d  (zero-guess first sweep: L1: s=1, d=l1 ; Jacobi: s=w, d=diag)
+void vec_scale_div(double* y, double s, const double* x, const double* d, size_t n,
+                   const Reduce& red = Reduce(), const int* done = nullptr);
+void vec_dot(const double* x, const double* y, size_t n, double* out_dev,
+             const int* done = nullptr);
+void vec_reduce(const double* x, size_t n, const Reduce& red, const int* done = nullptr);
+void vec_mul(double* y, const double* d, const double* x, size_t n, const int* done = nullptr);
+void scaling_alpha(double* s3, const int* done = nullptr);   // s[0] = min(s[1]/s[2], 1)
+// host-returning reductions (synchronise): used by drop-in level-1 calls and tests
+double vec_dot_host(const double* x, const double* y, size_t n);
+double vec_norm2_host(const double* x, size_t n);
+
+// grid-reduction scratch: returns partial buffer large enough for `nblocks` CTAs x 2 sums
+double*       red_partials(size_t nblocks);
+unsigned int* red_ticket();
+
+// ------------------------------------------------------------------------------------
+// timing helpers
+// ------------------------------------------------------------------------------------
+void flush_l2();
+
+} // namespace fc
+
+// ------------------------------------------------------------------------------------
+// CUDA-graph capture of a fixed kernel sequence issued on ctx().stream
+// ------------------------------------------------------------------------------------
+namespace fc {
+struct CapturedGraph {
+    cudaGraph_t     graph   = nullptr;
+    cudaGraphExec_t exec    = nullptr;
+    long long       kernels = 0;
+    ~CapturedGraph() { reset(); }
+    void reset()
+    {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        exec  = nullptr;
+        graph = nullptr;
+    }
+    // First call captures `f` (stream capture, nothing executes) and instantiates it; every
+    // call then launches the instantiated graph. With enable == false, f runs directly.
+    template <class F> void run(bool enable, F&& f)
+    {
+        Ctx& c = ctx();
+        if (!enable) {
+            f();
+            return;
+        }
+        if (!exec) {
+            c.capturing = true;
+            c.captured  = 0;
+            cudaError_t e = cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal);
+            if (e != cudaSuccess) {
+                c.capturing = false;
+                FC_CUDA(e);
+            }
+            try {
+                f();
+            } catch (...) {
+                cudaGraph_t tmp = nullptr;
+                cudaStreamEndCapture(c.stream, &tmp);
+                if (tmp) cudaGraphDestroy(tmp);
+                c.capturing = false;
+                throw;
+            }
+            c.capturing = false;
+            FC_CUDA(cudaStreamEndCapture(c.stream, &graph));
+            kernels = c.captured;
+            FC_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        }
+        FC_CUDA(cudaGraphLaunch(exec, c.stream));
+        c.launches += kernels;
+    }
+};
+} // namespace fc

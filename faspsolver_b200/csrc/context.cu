@@ -1,0 +1,119 @@
+// context.cu — process context, error plumbing, device memory, reduction scratch.
+#include "common.cuh"
+#include <cstdarg>
+#include <mutex>
+
+namespace fc {
+
+static thread_local std::string g_last_error;
+
+void        set_last_error(const std::string& s) { g_last_error = s; }
+const char* last_error() { return g_last_error.c_str(); }
+
+void fail(int code, const char* fmt, ...)
+{
+    char    buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    throw Error{code, std::string(buf)};
+}
+
+Ctx& ctx()
+{
+    static Ctx c;
+    return c;
+}
+
+void ensure_init()
+{
+    Ctx& c = ctx();
+    if (c.inited) return;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fail(ERROR_SOLVER_MISC,
+             "libfasp_cuda: no CUDA device available (%s) - this library has no CPU fallback",
+             e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    int dev = c.device;
+    const char* lr = getenv("LOCAL_RANK");
+    if (!c.inited && lr != nullptr && getenv("FASP_CUDA_DEVICE") == nullptr && dev == 0)
+        dev = atoi(lr) % ndev;
+    if (const char* fd = getenv("FASP_CUDA_DEVICE")) dev = atoi(fd);
+    if (dev < 0 || dev >= ndev) fail(ERROR_INPUT_PAR, "device %d out of range (0..%d)", dev, ndev - 1);
+    FC_CUDA(cudaSetDevice(dev));
+    c.device = dev;
+    cudaDeviceProp p;
+    FC_CUDA(cudaGetDeviceProperties(&p, dev));
+    c.sm_count = p.multiProcessorCount;
+    c.l2_bytes = (size_t)p.l2CacheSize;
+    FC_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.red_ticket = dalloc<unsigned int>(4);
+    FC_CUDA(cudaMemset(c.red_ticket, 0, 4 * sizeof(unsigned int)));
+    c.inited = true;
+    if (const char* s = getenv("FASP_CUDA_STRICT")) c.opt.strict = atoi(s);
+    if (const char* s = getenv("FASP_CUDA_GRAPH")) c.opt.graph = atoi(s);
+    if (const char* s = getenv("FASP_CUDA_COARSE_DENSE")) c.opt.coarse_dense = atoi(s);
+    if (const char* s = getenv("FASP_CUDA_ZERO_GUESS")) c.opt.zero_guess = atoi(s);
+}
+
+void* dmalloc(size_t bytes)
+{
+    if (bytes == 0) bytes = 8;
+    void*       p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(ERROR_ALLOC_MEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return p;
+}
+
+void dfree(void* p)
+{
+    if (p) cudaFree(p);
+}
+
+// The partial buffer only ever grows, and superseded buffers stay alive: captured CUDA
+// graphs may still hold their address.
+double* red_partials(size_t nblocks)
+{
+    Ctx&   c    = ctx();
+    size_t need = 4 * nblocks + 16;   // up to 4 sums per CTA
+    if (need > c.red_cap) {
+        if (c.capturing)
+            fail(ERROR_SOLVER_MISC, "reduction scratch must be reserved before graph capture");
+        size_t cap = c.red_cap ? c.red_cap : (size_t)1 << 16;
+        while (cap < need) cap *= 2;
+        c.red_partials = dalloc<double>(cap);   // old buffer intentionally kept
+        c.red_cap      = cap;
+    }
+    return c.red_partials;
+}
+
+unsigned int* red_ticket() { return ctx().red_ticket; }
+
+__global__ void flush_kernel(char* buf, size_t n, char v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = i * 16; k + 16 <= n; k += stride * 16)
+        *reinterpret_cast<int4*>(buf + k) = make_int4(v, v, v, v);
+}
+
+void flush_l2()
+{
+    Ctx& c = ctx();
+    if (!c.flush_buf) {
+        c.flush_bytes = 2 * c.l2_bytes > ((size_t)256 << 20) ? 2 * c.l2_bytes : ((size_t)256 << 20);
+        c.flush_buf   = static_cast<char*>(dmalloc(c.flush_bytes));
+    }
+    static char v = 0;
+    flush_kernel<<<c.sm_count * 8, 256, 0, c.stream>>>(c.flush_buf, c.flush_bytes, ++v);
+    FC_CUDA(cudaPeekAtLastError());
+}
+
+} // namespace fc

@@ -1,0 +1,471 @@
+// krylov.cu — PCG on the device, no host round-trip per iteration.
+//
+// Replaces fasp_solver_dcsr_pcg / fasp_solver_dbsr_pcg (KryPcg.c:96-362, :386) including the
+// reference's safeguards: division guard (:172-177), slow-convergence / stagnation restart
+// (:212-274), false-convergence re-check with the true residual (:277-324).
+//
+// All scalars (alpha, beta, norms, flags, iteration counter) live in a PcgState struct in
+// HBM. One iteration is a fixed sequence of kernels; data-dependent branches of the CPU loop
+// become kernels that are gated by device flags (`skip_*`, `done`) and return at once when
+// their branch is not taken. The sequence is captured once into a CUDA graph and replayed;
+// the host enqueues iterations `lookahead` ahead of the (asynchronous, pinned-memory) status
+// read, so the GPU never waits for the host and the iterates are identical to a loop that
+// tests convergence synchronously.
+#include "krylov.cuh"
+#include "reduce.cuh"
+
+namespace fc {
+
+// ------------------------------------------------------------------------------------
+// host-callback preconditioner
+// ------------------------------------------------------------------------------------
+HostPrec::HostPrec(precond* pc_, size_t n_) : pc(pc_), n(n_)
+{
+    FC_CUDA(cudaMallocHost(&hr, sizeof(double) * n));
+    FC_CUDA(cudaMallocHost(&hz, sizeof(double) * n));
+}
+HostPrec::~HostPrec()
+{
+    cudaFreeHost(hr);
+    cudaFreeHost(hz);
+}
+void HostPrec::apply(const double* r, double* z, const Reduce& red, const int* done)
+{
+    Ctx& c = ctx();
+    FC_CUDA(cudaMemcpyAsync(hr, r, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+    FC_CUDA(cudaStreamSynchronize(c.stream));
+    pc->fct(hr, hz, pc->data);
+    FC_CUDA(cudaMemcpyAsync(z, hz, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    vec_reduce(z, n, red, done);
+}
+
+// ------------------------------------------------------------------------------------
+// printing (same text as the reference)
+// ------------------------------------------------------------------------------------
+void print_itinfo(int prtlvl, int stop_type, int iter, double relres, double absres,
+                  double factor)
+{
+    if (prtlvl < PRINT_SOME) return;
+    if (iter > 0) {
+        printf("%6d | %13.6e   | %13.6e  | %10.4f\n", iter, relres, absres, factor);
+    } else {
+        printf("-----------------------------------------------------------\n");
+        switch (stop_type) {
+            case STOP_REL_RES:
+                printf("It Num |   ||r||/||b||   |     ||r||      |  Conv. Factor\n");
+                break;
+            case STOP_REL_PRECRES:
+                printf("It Num | ||r||_B/||b||_B |    ||r||_B     |  Conv. Factor\n");
+                break;
+            case STOP_MOD_REL_RES:
+                printf("It Num |   ||r||/||x||   |     ||r||      |  Conv. Factor\n");
+                break;
+        }
+        printf("-----------------------------------------------------------\n");
+        printf("%6d | %13.6e   | %13.6e  |     -.-- \n", iter, relres, absres);
+    }
+}
+void print_final(int iter, int maxit, double relres)
+{
+    if (iter > maxit)
+        printf("### WARNING: MaxIt = %d reached with relative residual %.10e.\n", maxit, relres);
+    else if (iter >= 0)
+        printf("Number of iterations = %d with relative residual %.10e.\n", iter, relres);
+}
+
+// ------------------------------------------------------------------------------------
+// PCG
+// ------------------------------------------------------------------------------------
+struct PcgState {
+    double temp1, tp, zr, rr, alpha, beta;
+    double absres0, absres, relres, normr0, normu, factor, reldiff;
+    double uinf, uu, pp;
+    double tol, abstol, maxdiff;
+    int    iter, maxit, stop_type;
+    int    done, status, converged;
+    int    skip_stag, skip_stag2, skip_cand;
+    int    zero_p, stag, more_step;
+    int    divzero, n_stag_restart, n_false_conv;
+    int    hist_cap;
+};
+
+__device__ __forceinline__ void pcg_finish(PcgState* st, int status)
+{
+    st->status     = status;
+    st->done       = 1;
+    st->skip_stag  = 1;
+    st->skip_stag2 = 1;
+    st->skip_cand  = 1;
+}
+
+// after r0 = b - A u0, z0 = B r0 (KryPcg.c:125-162)
+__global__ void k_pcg_init(PcgState* st, double* hr, double* ha, double* hf)
+{
+    double absres0, relres;
+    if (st->stop_type == STOP_MOD_REL_RES) {
+        absres0    = sqrt(st->rr);
+        st->normu  = fmax(SMALLREAL, sqrt(st->uu));
+        relres     = absres0 / st->normu;
+        st->normr0 = absres0;
+    } else {
+        absres0    = sqrt(st->rr);
+        st->normr0 = fmax(SMALLREAL, absres0);
+        relres     = absres0 / st->normr0;
+    }
+    st->absres0 = absres0;
+    st->absres  = absres0;
+    st->relres  = relres;
+    st->temp1   = st->zr;
+    hr[0]       = relres;
+    ha[0]       = absres0;
+    hf[0]       = 0.0;
+    if (relres < st->tol || absres0 < st->abstol) {
+        st->converged = 1;
+        pcg_finish(st, 0);
+    }
+}
+
+// u += alpha p ; r -= alpha t ; rr = ||r||^2          (KryPcg.c:171-188)
+__global__ void __launch_bounds__(256)
+k_pcg_update(PcgState* st, const double* __restrict__ p, const double* __restrict__ t,
+             double* __restrict__ u, double* __restrict__ r, size_t n, double* partials,
+             unsigned int* ticket)
+{
+    if (st->done) return;
+    const double tp = st->tp;
+    double       v[1] = {0.0};
+    if (fabs(tp) > SMALLREAL2) {
+        const double alpha = st->temp1 / tp;
+        const double nalpha = -alpha;
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n;
+             i += (size_t)gridDim.x * 256) {
+            u[i]            = __dadd_rn(u[i], __dmul_rn(alpha, p[i]));
+            const double ri = __dadd_rn(r[i], __dmul_rn(nalpha, t[i]));
+            r[i]            = ri;
+            v[0] += ri * ri;
+        }
+    }
+    grid_reduce<1, 0>(v, partials, ticket, [&](const double* s) { st->rr = s[0]; });
+}
+
+// scalar part of one iteration up to the slow-convergence test (KryPcg.c:165-212)
+__global__ void k_pcg_check(PcgState* st, double* hr, double* ha, double* hf)
+{
+    if (st->done) return;
+    st->iter += 1;
+    if (!(fabs(st->tp) > SMALLREAL2)) {   // possible breakdown
+        st->divzero = 1;
+        pcg_finish(st, 0);
+        return;
+    }
+    st->alpha  = st->temp1 / st->tp;
+    st->absres = sqrt(st->rr);
+    st->relres = st->absres / (st->stop_type == STOP_MOD_REL_RES ? st->normu : st->normr0);
+    st->factor = st->absres / st->absres0;
+    if (st->iter < st->hist_cap) {
+        hr[st->iter] = st->relres;
+        ha[st->iter] = st->absres;
+        hf[st->iter] = st->factor;
+    }
+    st->skip_stag2 = 1;
+    if (st->factor > 0.9) {
+        st->skip_stag = 0;
+        st->skip_cand = 1;
+    } else {
+        st->skip_stag = 1;
+        st->skip_cand = !(st->relres < st->tol);
+    }
+}
+
+// ||u||_inf, ||u||^2, ||p||^2 (only when converging slowly, KryPcg.c:215-225)
+__global__ void __launch_bounds__(256)
+k_pcg_stag_norms(PcgState* st, const double* __restrict__ u, const double* __restrict__ p,
+                 size_t n, double* partials, unsigned int* ticket)
+{
+    if (st->skip_stag) return;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const double ui = u[i], pi = p[i];
+        v[0] = fmax(v[0], fabs(ui));
+        v[1] += ui * ui;
+        v[2] += pi * pi;
+    }
+    grid_reduce<3, 1>(v, partials, ticket, [&](const double* s) {
+        st->uinf = s[0];
+        st->uu   = s[1];
+        st->pp   = s[2];
+    });
+}
+
+// Check I and the decision of Check II (KryPcg.c:215-227)
+__global__ void k_pcg_stag_check(PcgState* st)
+{
+    if (st->done || st->skip_stag) return;
+    st->skip_stag = 1;
+    if (st->uinf <= SMALLREAL) {
+        pcg_finish(st, ERROR_SOLVER_SOLSTAG);
+        return;
+    }
+    st->normu   = sqrt(st->uu);
+    st->reldiff = fabs(st->alpha) * sqrt(st->pp) / st->normu;
+    if ((st->stag <= MAX_STAG) & (st->reldiff < st->maxdiff)) {
+        st->skip_stag2 = 0;   // restart: recompute r = b - A u
+    } else {
+        st->skip_cand = !(st->relres < st->tol);
+    }
+}
+
+// after the stagnation restart's true residual (KryPcg.c:236-270)
+__global__ void k_pcg_stag_check2(PcgState* st)
+{
+    if (st->done || st->skip_stag2) return;
+    st->skip_stag2 = 1;
+    st->n_stag_restart += 1;
+    st->absres = sqrt(st->rr);
+    st->relres = st->absres / (st->stop_type == STOP_MOD_REL_RES ? st->normu : st->normr0);
+    if (st->relres < st->tol) {
+        st->converged = 1;
+        pcg_finish(st, 0);
+    } else if (st->stag >= MAX_STAG) {
+        pcg_finish(st, ERROR_SOLVER_STAG);
+    } else {
+        st->zero_p = 1;
+        st->stag += 1;
+    }
+}
+
+// Check III after the true residual has been recomputed (KryPcg.c:277-327)
+__global__ void k_pcg_cand_check(PcgState* st)
+{
+    if (st->done) return;
+    if (!st->skip_cand) {
+        st->skip_cand = 1;
+        st->absres    = sqrt(st->rr);
+        st->relres = st->absres / (st->stop_type == STOP_MOD_REL_RES ? st->normu : st->normr0);
+        if (st->relres < st->tol) {
+            st->converged = 1;
+            pcg_finish(st, 0);
+            return;
+        }
+        st->n_false_conv += 1;
+        if (st->more_step >= MAX_RESTART) {
+            pcg_finish(st, ERROR_SOLVER_TOLSMALL);
+            return;
+        }
+        st->zero_p = 1;
+        st->more_step += 1;
+    }
+    st->absres0 = st->absres;   // save residual for next iteration (:327)
+}
+
+// p = z + beta p with beta = (z,r)/(z_old,r_old)            (KryPcg.c:337-343)
+__global__ void __launch_bounds__(256)
+k_pcg_direction(const PcgState* st, const double* __restrict__ z, double* __restrict__ p,
+                size_t n)
+{
+    if (st->done) return;
+    const double beta = st->zr / st->temp1;
+    const bool   zp   = st->zero_p != 0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const double pi = zp ? 0.0 : p[i];
+        p[i]            = __dadd_rn(z[i], __dmul_rn(beta, pi));
+    }
+}
+__global__ void k_pcg_end(PcgState* st)
+{
+    if (st->done) return;
+    st->beta   = st->zr / st->temp1;
+    st->temp1  = st->zr;
+    st->zero_p = 0;
+    if (st->iter >= st->maxit) st->done = 1;   // host will report ERROR_SOLVER_MAXIT
+}
+
+static int vgrid(size_t n)
+{
+    size_t g   = (n + 1023) / 1024;
+    size_t cap = (size_t)ctx().sm_count * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+struct PinnedStatus {
+    int    done, iter, status, converged;
+    double relres;
+};
+
+int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double abstol,
+              int MaxIt, int StopType, int PrtLvl, SolveStats* stats)
+{
+    ensure_init();
+    Ctx&         c = ctx();
+    const size_t n = (size_t)A.n;
+    if (StopType != STOP_REL_RES && StopType != STOP_MOD_REL_RES)
+        fail(ERROR_INPUT_PAR,
+             "device PCG supports stop_type STOP_REL_RES (1) and STOP_MOD_REL_RES (3), got %d",
+             StopType);
+    if (PrtLvl > PRINT_NONE) printf("\nCalling CG solver (CSR) ...\n");
+
+    const long long launches0 = c.launches;
+    const int       hcap      = MaxIt + 2;
+    double*   work = dalloc<double>(4 * n + 3 * (size_t)hcap);
+    double *  p = work, *z = p + n, *r = z + n, *t = r + n;
+    double *  hr = t + n, *ha = hr + hcap, *hf = ha + hcap;
+    PcgState* st = dalloc<PcgState>(1);
+    PinnedStatus* pin = nullptr;
+    const int     look = c.opt.lookahead < 1 ? 1 : c.opt.lookahead;
+    FC_CUDA(cudaMallocHost(&pin, sizeof(PinnedStatus) * (look + 1)));
+    std::vector<cudaEvent_t> ev(look + 1);
+    for (auto& e : ev) FC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaEvent_t t0, t1;
+    FC_CUDA(cudaEventCreate(&t0));
+    FC_CUDA(cudaEventCreate(&t1));
+    CapturedGraph   graph;
+    int             ret = 0;
+
+    auto cleanup = [&]() {
+        graph.reset();
+        for (auto& e : ev) cudaEventDestroy(e);
+        cudaEventDestroy(t0);
+        cudaEventDestroy(t1);
+        cudaFreeHost(pin);
+        dfree(work);
+        dfree(st);
+    };
+
+    try {
+        PcgState h0;
+        memset(&h0, 0, sizeof(h0));
+        h0.tol = tol, h0.abstol = abstol, h0.maxdiff = tol * STAG_RATIO;
+        h0.maxit = MaxIt, h0.stop_type = StopType;
+        h0.stag = 1, h0.more_step = 1;
+        h0.skip_stag = h0.skip_stag2 = h0.skip_cand = 1;
+        h0.hist_cap = hcap;
+        h0.absres0 = h0.absres = h0.relres = h0.normu = h0.normr0 = BIGREAL;
+        FC_CUDA(cudaMemcpyAsync(st, &h0, sizeof(h0), cudaMemcpyHostToDevice, c.stream));
+        red_partials((size_t)c.sm_count * 8);
+        const int* done = &st->done;
+        const int  g    = vgrid(n);
+
+        FC_CUDA(cudaEventRecord(t0, c.stream));
+        // r = b - A u ; z = B r ; p = z ; temp1 = (z,r)
+        {
+            Reduce red;
+            red.nrm2_out = &st->rr;
+            A.apply(CSR_RESID, 1.0, u, b, r, red, nullptr);
+            if (StopType == STOP_MOD_REL_RES) {
+                Reduce ru;
+                ru.nrm2_out = &st->uu;
+                vec_reduce(u, n, ru, nullptr);
+            }
+            Reduce rz;
+            rz.dot_with = r;
+            rz.dot_out  = &st->zr;
+            pc.apply(r, z, rz, nullptr);
+            FC_LAUNCH(k_pcg_init, 1, 1, 0, st, hr, ha, hf);
+            vec_copy(p, z, n, done);
+        }
+
+        auto iteration = [&]() {
+            Reduce rt;   // t = A p, tp = (t,p)
+            rt.dot_with = p;
+            rt.dot_out  = &st->tp;
+            A.apply(CSR_MXV, 1.0, p, nullptr, t, rt, done);
+            FC_LAUNCH(k_pcg_update, g, 256, 0, st, p, t, u, r, n, red_partials(g), red_ticket());
+            FC_LAUNCH(k_pcg_check, 1, 1, 0, st, hr, ha, hf);
+            // slow convergence: stagnation test and possible restart
+            FC_LAUNCH(k_pcg_stag_norms, g, 256, 0, st, u, p, n, red_partials(g), red_ticket());
+            FC_LAUNCH(k_pcg_stag_check, 1, 1, 0, st);
+            Reduce rr;
+            rr.nrm2_out = &st->rr;
+            A.apply(CSR_RESID, 1.0, u, b, r, rr, &st->skip_stag2);
+            FC_LAUNCH(k_pcg_stag_check2, 1, 1, 0, st);
+            // false-convergence guard: true residual
+            A.apply(CSR_RESID, 1.0, u, b, r, rr, &st->skip_cand);
+            FC_LAUNCH(k_pcg_cand_check, 1, 1, 0, st);
+            // z = B r, zr = (z,r)
+            Reduce rz;
+            rz.dot_with = r;
+            rz.dot_out  = &st->zr;
+            pc.apply(r, z, rz, done);
+            FC_LAUNCH(k_pcg_direction, g, 256, 0, st, z, p, n);
+            FC_LAUNCH(k_pcg_end, 1, 1, 0, st);
+        };
+
+        const bool use_graph = c.opt.graph && pc.capturable();
+        int  launched = 0;
+        bool finished = false;
+        for (int it = 1; it <= MaxIt && !finished; ++it) {
+            graph.run(use_graph, iteration);
+            launched          = it;
+            const int slot    = it % (look + 1);
+            // status snapshot: {done, iter, status, converged} are contiguous ints
+            FC_CUDA(cudaMemcpyAsync(&pin[slot].done, &st->done, sizeof(int),
+                                    cudaMemcpyDeviceToHost, c.stream));
+            FC_CUDA(cudaEventRecord(ev[slot], c.stream));
+            if (it > look) {
+                const int old = (it - look) % (look + 1);
+                FC_CUDA(cudaEventSynchronize(ev[old]));
+                if (pin[old].done) finished = true;
+            }
+        }
+        (void)launched;
+        FC_CUDA(cudaEventRecord(t1, c.stream));
+        FC_CUDA(cudaStreamSynchronize(c.stream));
+
+        PcgState hs;
+        FC_CUDA(cudaMemcpy(&hs, st, sizeof(hs), cudaMemcpyDeviceToHost));
+        int iter = hs.iter;
+        if (!hs.converged && hs.status == 0 && !hs.divzero && hs.iter >= MaxIt) iter = MaxIt + 1;
+        if (stats || PrtLvl >= PRINT_SOME) {
+            const int           nh = (hs.iter + 1 < hcap) ? hs.iter + 1 : hcap;
+            std::vector<double> h3(3 * (size_t)hcap);
+            FC_CUDA(cudaMemcpy(h3.data(), hr, sizeof(double) * 3 * hcap, cudaMemcpyDeviceToHost));
+            if (PrtLvl >= PRINT_SOME)
+                for (int i = 0; i < nh; ++i)
+                    print_itinfo(PrtLvl, StopType, i, h3[i], h3[hcap + i], h3[2 * hcap + i]);
+            if (stats) {
+                stats->hist_relres.assign(h3.begin(), h3.begin() + nh);
+                stats->hist_absres.assign(h3.begin() + hcap, h3.begin() + hcap + nh);
+                stats->hist_factor.assign(h3.begin() + 2 * hcap, h3.begin() + 2 * hcap + nh);
+            }
+        }
+        if (hs.divzero && PrtLvl > PRINT_NONE)
+            printf("### WARNING: Divided by zero! [%s:%d]\n", __FUNCTION__, __LINE__);
+        if (PrtLvl >= PRINT_MORE && hs.n_false_conv)
+            printf("### WARNING: false convergence detected %d time(s); iteration restarted\n",
+                   hs.n_false_conv);
+        if (PrtLvl >= PRINT_MORE && hs.n_stag_restart)
+            printf("### WARNING: Iteration restarted -- stagnation! (%d time(s))\n",
+                   hs.n_stag_restart);
+        if (hs.status == ERROR_SOLVER_SOLSTAG && PrtLvl > PRINT_MIN)
+            printf("### WARNING: Iteration stopped -- solution almost zero! [%s:%d]\n",
+                   __FUNCTION__, __LINE__);
+        if (hs.status == ERROR_SOLVER_STAG && PrtLvl > PRINT_MIN)
+            printf("### WARNING: Iteration stopped -- staggnation! [%s:%d]\n", __FUNCTION__,
+                   __LINE__);
+        if (hs.status == ERROR_SOLVER_TOLSMALL && PrtLvl > PRINT_MIN)
+            printf("### WARNING: The tolerence might be too small! [%s:%d]\n", __FUNCTION__,
+                   __LINE__);
+        if (hs.status < 0) iter = hs.status;
+        if (PrtLvl > PRINT_NONE) print_final(iter, MaxIt, hs.relres);
+
+        float ms = 0.f;
+        FC_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+        if (stats) {
+            stats->iters    = hs.iter;
+            stats->relres   = hs.relres;
+            stats->ms       = ms;
+            stats->launches = c.launches - launches0;
+        }
+        ret = (iter > MaxIt) ? ERROR_SOLVER_MAXIT : iter;
+    } catch (...) {
+        cudaStreamSynchronize(c.stream);
+        cleanup();
+        throw;
+    }
+    cleanup();
+    return ret;
+}
+
+} // namespace fc

@@ -1,0 +1,89 @@
+// krylov.cuh — device-resident Krylov loops (PCG, GMRES(m), vGMRES) over abstract operators.
+#pragma once
+#include "common.cuh"
+#include "amg.cuh"
+
+namespace fc {
+
+// y = A x style operator on device vectors (CSR or BSR behind it)
+struct LinOp {
+    int n = 0;
+    virtual ~LinOp() {}
+    // mode: CSR_MXV / CSR_AXPY / CSR_RESID semantics
+    virtual void apply(int mode, double alpha, const double* x, const double* b, double* y,
+                       const Reduce& red, const int* done) = 0;
+};
+struct CsrOp : LinOp {
+    const DevCSR* A;
+    explicit CsrOp(const DevCSR* a) : A(a) { n = a->rows; }
+    void apply(int mode, double alpha, const double* x, const double* b, double* y,
+               const Reduce& red, const int* done) override
+    {
+        CsrArgs a;
+        a.mode  = mode;
+        a.alpha = alpha;
+        a.x     = x;
+        a.b     = b;
+        a.y     = y;
+        a.red   = red;
+        a.done  = done;
+        csr_launch(*A, a);
+    }
+};
+
+// z = B r on device vectors
+struct Prec {
+    virtual ~Prec() {}
+    virtual void apply(const double* r, double* z, const Reduce& red, const int* done) = 0;
+    virtual bool capturable() const { return true; }
+};
+struct IdentityPrec : Prec {
+    size_t n;
+    explicit IdentityPrec(size_t n_) : n(n_) {}
+    void apply(const double* r, double* z, const Reduce& red, const int* done) override
+    {
+        vec_copy(z, r, n, done);
+        vec_reduce(z, n, red, done);
+    }
+};
+struct AmgPrec : Prec {
+    Amg* h;
+    explicit AmgPrec(Amg* h_) : h(h_) {}
+    void apply(const double* r, double* z, const Reduce& red, const int* done) override
+    {
+        amg_apply(*h, r, z, red, done);
+    }
+};
+// arbitrary host callback pc->fct(r, z, data) with host pointers: D2H r, call, H2D z
+struct HostPrec : Prec {
+    precond* pc;
+    size_t   n;
+    double * hr = nullptr, *hz = nullptr;
+    HostPrec(precond* pc_, size_t n_);
+    ~HostPrec() override;
+    void apply(const double* r, double* z, const Reduce& red, const int* done) override;
+    bool capturable() const override { return false; }
+};
+
+struct SolveStats {
+    int       iters    = 0;
+    double    relres   = 0.0;
+    double    ms       = 0.0;     // device time of the Krylov loop (CUDA events)
+    long long launches = 0;
+    std::vector<double> hist_relres, hist_absres, hist_factor;
+};
+
+// All vectors are device pointers. Returns FASP status (>=0 iterations, <0 ERROR_*).
+int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double abstol,
+              int MaxIt, int StopType, int PrtLvl, SolveStats* stats);
+// restart > 0; variable == true -> Baker/Jessup/Kolev restart adaptation (KryPvgmres.c)
+int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, double abstol,
+                int MaxIt, int restart, int StopType, int PrtLvl, bool variable,
+                SolveStats* stats);
+
+// FASP's iteration table / final line (AuxMessage.c:41-76, KryUtil.inl:93-103)
+void print_itinfo(int prtlvl, int stop_type, int iter, double relres, double absres,
+                  double factor);
+void print_final(int iter, int maxit, double relres);
+
+} // namespace fc

@@ -1,0 +1,173 @@
+// solver.cu — solver objects: an uploaded hierarchy plus the device Krylov loop.
+// Mirrors the wiring of fasp_solver_dcsr_krylov_amg (SolCSR.c:476-569) and
+// fasp_solver_dcsr_itsolver (SolCSR.c:56-140) with the setup phase factored out, and the
+// AMG-as-solver loop fasp_amg_solve (PreMGSolve.c:49-135).
+#include "solver.cuh"
+#include "reduce.cuh"
+
+namespace fc {
+
+fasp_cuda_solver_s* solver_create_csr(AMG_data* mgl, AMG_param* amgparam)
+{
+    ensure_init();
+    fasp_cuda_solver_s* s = new fasp_cuda_solver_s();
+    try {
+        AMG_param p = *amgparam;
+        p.tol       = 1e-6;   // fasp_precond_amg re-initialises tol (PreCSR.c:425, AuxParam.c:437)
+        s->amg      = amg_upload(mgl, &p);
+        s->n        = (size_t)s->amg->lv[0].n;
+        s->d_b      = dalloc<double>(s->n);
+        s->d_x      = dalloc<double>(s->n);
+        FC_CUDA(cudaMallocHost(&s->pin, sizeof(double) * 2 * s->n));
+    } catch (...) {
+        solver_destroy(s);
+        throw;
+    }
+    return s;
+}
+
+void solver_destroy(fasp_cuda_solver_s* s)
+{
+    if (!s) return;
+    amg_free(s->amg);
+    dfree(s->d_b);
+    dfree(s->d_x);
+    if (s->pin) cudaFreeHost(s->pin);
+    delete s;
+}
+
+int solver_solve_dev(fasp_cuda_solver_s* s, const double* b_dev, double* x_dev, ITS_param* it)
+{
+    if (!s || !s->amg) fail(ERROR_INPUT_PAR, "null solver");
+    CsrOp   op(&s->amg->lv[0].A);
+    AmgPrec pc(s->amg);
+    switch (it->itsolver_type) {
+        case SOLVER_CG:
+            return pcg_solve(op, b_dev, x_dev, pc, it->tol, it->abstol, it->maxit, it->stop_type,
+                             it->print_level, &s->stats);
+        case SOLVER_GMRES:
+            return gmres_solve(op, b_dev, x_dev, pc, it->tol, it->abstol, it->maxit, it->restart,
+                               it->stop_type, it->print_level, false, &s->stats);
+        case SOLVER_VGMRES:
+            return gmres_solve(op, b_dev, x_dev, pc, it->tol, it->abstol, it->maxit, it->restart,
+                               it->stop_type, it->print_level, true, &s->stats);
+        default:
+            fail(ERROR_SOLVER_TYPE,
+                 "itsolver_type %d not on the device path (supported: CG 1, GMRES 4, VGMRES 5)",
+                 (int)it->itsolver_type);
+    }
+}
+
+int solver_solve_host(fasp_cuda_solver_s* s, const double* b, double* x, ITS_param* it)
+{
+    if (!s || !s->amg) fail(ERROR_INPUT_PAR, "null solver");
+    Ctx&         c = ctx();
+    const size_t n = s->n;
+    cudaEvent_t  e0, e1;
+    FC_CUDA(cudaEventCreate(&e0));
+    FC_CUDA(cudaEventCreate(&e1));
+    int ret = 0;
+    try {
+        // pageable caller memory -> pinned staging -> HBM (and back)
+        FC_CUDA(cudaEventRecord(e0, c.stream));
+        memcpy(s->pin, b, sizeof(double) * n);
+        memcpy(s->pin + n, x, sizeof(double) * n);
+        FC_CUDA(cudaMemcpyAsync(s->d_b, s->pin, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+        FC_CUDA(cudaMemcpyAsync(s->d_x, s->pin + n, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+        ret = solver_solve_dev(s, s->d_b, s->d_x, it);
+        FC_CUDA(cudaMemcpyAsync(s->pin + n, s->d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+        FC_CUDA(cudaEventRecord(e1, c.stream));
+        FC_CUDA(cudaStreamSynchronize(c.stream));
+        memcpy(x, s->pin + n, sizeof(double) * n);
+        float ms = 0.f;
+        FC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        s->ms_total = ms;
+    } catch (...) {
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        throw;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ret;
+}
+
+double solver_stat(const fasp_cuda_solver_s* s, int what)
+{
+    if (!s) return -1.0;
+    switch (what) {
+        case 0: return (double)s->stats.iters;
+        case 1: return s->stats.relres;
+        case 2: return s->stats.ms;
+        case 3: return (double)s->stats.launches;
+        case 4: return s->ms_total;
+        default: return -1.0;
+    }
+}
+
+int solver_history(const fasp_cuda_solver_s* s, double* relres, int max_entries)
+{
+    if (!s || !relres) return 0;
+    int n = (int)s->stats.hist_relres.size();
+    if (n > max_entries) n = max_entries;
+    for (int i = 0; i < n; ++i) relres[i] = s->stats.hist_relres[i];
+    return n;
+}
+
+void amg_smooth_only(Amg& h, const double* b, double* u, int nsweeps);
+
+// fasp_amg_solve (PreMGSolve.c:49-135): cycles until ||b - A x|| / ||b|| < tol
+int solver_amg_solve(AMG_data* mgl, AMG_param* param)
+{
+    ensure_init();
+    Ctx&      c      = ctx();
+    const int MaxIt  = param->maxit;
+    const int prtlvl = param->print_level;
+    Amg*      h      = amg_upload(mgl, param);
+    int       iter   = 0;
+    double    relres1 = 1.0;
+    double*   work   = nullptr;
+    double*   scal   = nullptr;
+    try {
+        const size_t n = h->lv[0].n;
+        work           = dalloc<double>(3 * n);
+        scal           = dalloc<double>(2);
+        double *b = work, *x = work + n, *r = work + 2 * n;
+        FC_CUDA(cudaMemcpyAsync(b, mgl[0].b.val, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+        FC_CUDA(cudaMemcpyAsync(x, mgl[0].x.val, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+        const double sumb    = vec_norm2_host(b, n);
+        double       absres0 = sumb, absres, factor;
+        print_itinfo(prtlvl, STOP_REL_RES, iter, relres1, sumb, 0.0);
+        if (sumb <= SMALLREAL) vec_set(x, 0.0, n);
+        CsrOp op(&h->lv[0].A);
+        while ((iter++ < MaxIt) & (sumb > SMALLREAL)) {
+            amg_cycle_inplace(*h, b, x, false, Reduce(), nullptr);
+            Reduce red;
+            red.nrm2_out = scal;
+            op.apply(CSR_RESID, 1.0, x, b, r, red, nullptr);
+            double rr = 0.0;
+            FC_CUDA(cudaMemcpyAsync(&rr, scal, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+            FC_CUDA(cudaStreamSynchronize(c.stream));
+            absres  = sqrt(rr);
+            relres1 = absres / fmax(SMALLREAL, sumb);
+            factor  = absres / absres0;
+            absres0 = absres;
+            print_itinfo(prtlvl, STOP_REL_RES, iter, relres1, absres, factor);
+            if (relres1 < param->tol) break;
+        }
+        FC_CUDA(cudaMemcpyAsync(mgl[0].x.val, x, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+        FC_CUDA(cudaStreamSynchronize(c.stream));
+        if (prtlvl > PRINT_NONE) print_final(iter, MaxIt, relres1);
+    } catch (...) {
+        dfree(work);
+        dfree(scal);
+        amg_free(h);
+        throw;
+    }
+    dfree(work);
+    dfree(scal);
+    amg_free(h);
+    return (iter > MaxIt) ? ERROR_SOLVER_MAXIT : iter;
+}
+
+} // namespace fc

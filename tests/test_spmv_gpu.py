@@ -1,0 +1,116 @@
+"""CSR SpMV parity: libfasp_cuda (C ABI) vs the sequential reference, same inputs.
+Bar (north star): |y - y_ref|_i <= 1e-14 * (|A||x|)_i ; rows handled by one thread are bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from faspsolver_b200 import fasp_types as T
+from faspsolver_b200 import problems as PB
+from faspsolver_b200.fasp_types import CSR
+
+pytestmark = pytest.mark.gpu
+
+
+def _bound(A, x):
+    return np.abs(A.to_scipy()) @ np.abs(x)
+
+
+def _cases(data):
+    rng = np.random.default_rng(3)
+    out = [("FD", data["FD"]), ("FE", data["FE"]), ("p7_24", PB.poisson7(24)), ("p27_12", PB.poisson27(12)),
+           ("cd7_16", PB.convdiff7(16))]
+    # irregular rows incl. empty rows, rows of 40..300 and one row longer than any CTA tile
+    m = sp.random(700, 900, density=0.02, format="lil", random_state=5)
+    m[10, :] = rng.uniform(-1, 1, 900)
+    m[11, :300] = rng.uniform(-1, 1, 300)
+    m[500:520, :] = 0
+    out.append(("irregular", CSR.from_scipy(m.tocsr())))
+    big = sp.random(3, 9000, density=0.9, format="csr", random_state=6)
+    out.append(("longrow", CSR.from_scipy(big)))
+    dense_rows = sp.random(64, 2000, density=0.5, format="csr", random_state=8)
+    out.append(("rows1000", CSR.from_scipy(dense_rows)))
+    return out
+
+
+def test_mxv_matches_reference(gpu, ref, data):
+    rng = np.random.default_rng(11)
+    for name, A in _cases(data):
+        x = rng.uniform(-1, 1, A.shape[1])
+        y = np.empty(A.shape[0])
+        st = gpu.fasp_cuda_blas_dcsr_mxv(A.ptr(), T.as_preal(x), T.as_preal(y))
+        assert st == 0, gpu.fasp_cuda_last_error()
+        yr = ref.mxv(A, x)
+        err = np.abs(y - yr)
+        assert np.all(err <= 1e-14 * _bound(A, x) + 1e-300), (name, err.max())
+
+
+def test_mxv_short_rows_bit_exact(gpu, ref, data):
+    """Rows reduced by a single thread follow the CPU order and rounding exactly."""
+    rng = np.random.default_rng(12)
+    for name, A in (("FE", data["FE"]), ("p7_24", PB.poisson7(24)), ("p27_12", PB.poisson27(12))):
+        x = rng.uniform(-1, 1, A.shape[1])
+        y = np.empty(A.shape[0])
+        assert gpu.fasp_cuda_blas_dcsr_mxv(A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
+        assert np.array_equal(y, ref.mxv(A, x)), name
+
+
+def test_strict_mode_bit_exact_everywhere(gpu, ref, data):
+    rng = np.random.default_rng(13)
+    gpu.fasp_cuda_set_option(b"strict", 1.0)
+    try:
+        for name, A in _cases(data):
+            x = rng.uniform(-1, 1, A.shape[1])
+            y = np.empty(A.shape[0])
+            assert gpu.fasp_cuda_blas_dcsr_mxv(A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
+            assert np.array_equal(y, ref.mxv(A, x)), name
+    finally:
+        gpu.fasp_cuda_set_option(b"strict", 0.0)
+
+
+@pytest.mark.parametrize("alpha", [1.0, -1.0, 0.37])
+def test_aAxpy_matches_reference(gpu, ref, data, alpha):
+    rng = np.random.default_rng(14)
+    for name, A in _cases(data):
+        x = rng.uniform(-1, 1, A.shape[1])
+        y0 = rng.uniform(-1, 1, A.shape[0])
+        y = y0.copy()
+        assert gpu.fasp_cuda_blas_dcsr_aAxpy(alpha, A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
+        yr = ref.aAxpy(alpha, A, x, y0)
+        err = np.abs(y - yr)
+        assert np.all(err <= 1e-14 * (abs(alpha) * _bound(A, x) + np.abs(y0)) + 1e-300), (name, err.max())
+
+
+def test_pattern_only_variants(gpu, ref, data):
+    rng = np.random.default_rng(15)
+    A = data["FE"]
+    x = rng.uniform(-1, 1, A.shape[1])
+    y, yr = np.empty(A.shape[0]), np.empty(A.shape[0])
+    assert gpu.fasp_cuda_blas_dcsr_mxv_agg(A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
+    ref.L.fasp_blas_dcsr_mxv_agg(A.ptr(), T.as_preal(x), T.as_preal(yr))
+    assert np.array_equal(y, yr)
+    y0 = rng.uniform(-1, 1, A.shape[0])
+    y, yr = y0.copy(), y0.copy()
+    assert gpu.fasp_cuda_blas_dcsr_aAxpy_agg(-0.5, A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
+    ref.L.fasp_blas_dcsr_aAxpy_agg(-0.5, A.ptr(), T.as_preal(x), T.as_preal(yr))
+    assert np.allclose(y, yr, rtol=0, atol=1e-13)
+
+
+def test_golden_vectors(gpu, data, golden_vectors):
+    """Against the committed reference outputs (no reference library needed)."""
+    A, g = data["FE"], golden_vectors
+    y = np.empty(A.shape[0])
+    assert gpu.fasp_cuda_blas_dcsr_mxv(A.ptr(), T.as_preal(np.ascontiguousarray(g["x"])), T.as_preal(y)) == 0
+    assert np.array_equal(y, g["mxv"])
+    y = data["FE_b"].copy()
+    assert gpu.fasp_cuda_blas_dcsr_aAxpy(-1.0, A.ptr(), T.as_preal(np.ascontiguousarray(g["x"])), T.as_preal(y)) == 0
+    assert np.array_equal(y, g["aAxpy_m1"])
+
+
+def test_empty_and_tiny(gpu):
+    A = CSR(3, 3, [0, 0, 1, 1], [2], [2.5])
+    y = np.full(3, 9.0)
+    x = np.array([1.0, 2.0, 3.0])
+    assert gpu.fasp_cuda_blas_dcsr_mxv(A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
+    assert np.array_equal(y, [0.0, 7.5, 0.0])
