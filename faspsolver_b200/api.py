@@ -47,6 +47,7 @@ def lib():
         "fasp_cuda_launch_count": (C.c_longlong, []),
         "fasp_cuda_launch_count_reset": (None, []),
         "fasp_cuda_set_option": (INT, [C.c_char_p, C.c_double]),
+        "fasp_cuda_profile_dump": (C.c_longlong, [C.c_char_p, C.c_longlong]),
         "fasp_cuda_get_option": (C.c_double, [C.c_char_p]),
         "fasp_cuda_blas_dcsr_mxv": (INT, [P(dCSRmat), PREAL, PREAL]),
         "fasp_cuda_blas_dcsr_aAxpy": (INT, [REAL, P(dCSRmat), PREAL, PREAL]),

@@ -154,6 +154,7 @@ static int* option_slot(const char* key)
     if (!strcmp(key, "graph")) return &o.graph;
     if (!strcmp(key, "zero_guess")) return &o.zero_guess;
     if (!strcmp(key, "lookahead")) return &o.lookahead;
+    if (!strcmp(key, "profile")) return &o.profile;
     return nullptr;
 }
 INT fasp_cuda_set_option(const char* key, double value)
@@ -170,6 +171,31 @@ double fasp_cuda_get_option(const char* key)
 {
     int* s = option_slot(key);
     return s ? (double)*s : -1.0;
+}
+
+// Profile records since the last call, one text line per launch:
+//   "<kind> <rows> <nnz> <ms> <algorithmic bytes>"  (kind = CsrMode, 100 = dense GEMV, 2xx = BSR)
+// Returns the number of characters written (truncated to cap-1).
+long long fasp_cuda_profile_dump(char* buf, long long cap)
+{
+    Ctx& c = ctx();
+    if (c.inited) cudaStreamSynchronize(c.stream);
+    std::string out;
+    char        line[160];
+    for (auto& r : c.prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        snprintf(line, sizeof(line), "%d %d %lld %.6f %.0f\n", r.kind, r.rows, r.nnz, ms, r.bytes);
+        out += line;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    c.prof.clear();
+    if (!buf || cap <= 0) return (long long)out.size();
+    long long n = (long long)out.size() < cap - 1 ? (long long)out.size() : cap - 1;
+    memcpy(buf, out.data(), (size_t)n);
+    buf[n] = 0;
+    return n;
 }
 
 // ------------------------------------------------------------------------------------

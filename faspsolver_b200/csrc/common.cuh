@@ -54,6 +54,7 @@ struct Options {
     int    graph            = 1;
     int    zero_guess       = 1;
     int    lookahead        = 2;   // Krylov iterations enqueued ahead of the status read
+    int    profile          = 0;   // record CUDA events around every matrix kernel (no graphs)
 };
 
 struct Ctx {
@@ -70,6 +71,14 @@ struct Ctx {
     double*       red_partials = nullptr;
     size_t        red_cap      = 0;
     unsigned int* red_ticket   = nullptr;
+    // per-launch profile records (opt.profile): tag, events, algorithmic bytes
+    struct ProfRec {
+        cudaEvent_t e0, e1;
+        int         kind, rows;
+        long long   nnz;
+        double      bytes;
+    };
+    std::vector<ProfRec> prof;
     // L2 flush buffer for timing helpers
     char*  flush_buf   = nullptr;
     size_t flush_bytes = 0;
@@ -84,6 +93,13 @@ void ensure_init();
         if (c__.capturing) c__.captured++; else c__.launches++;                            \
         FC_CUDA(cudaPeekAtLastError());                                                    \
     } while (0)
+
+// profiling scope: records events around the enclosed launches when opt.profile is on
+struct ProfScope {
+    bool on;
+    ProfScope(int kind, int rows, long long nnz, double bytes);
+    ~ProfScope();
+};
 
 // device allocation helpers (throw ERROR_ALLOC_MEM)
 void* dmalloc(size_t bytes);

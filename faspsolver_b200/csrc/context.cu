@@ -77,6 +77,23 @@ void dfree(void* p)
     if (p) cudaFree(p);
 }
 
+ProfScope::ProfScope(int kind, int rows, long long nnz, double bytes)
+{
+    Ctx& c = ctx();
+    on     = c.opt.profile && !c.capturing;
+    if (!on) return;
+    Ctx::ProfRec r;
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    r.kind = kind, r.rows = rows, r.nnz = nnz, r.bytes = bytes;
+    cudaEventRecord(r.e0, c.stream);
+    c.prof.push_back(r);
+}
+ProfScope::~ProfScope()
+{
+    if (on) cudaEventRecord(ctx().prof.back().e1, ctx().stream);
+}
+
 // The partial buffer only ever grows, and superseded buffers stay alive: captured CUDA
 // graphs may still hold their address.
 double* red_partials(size_t nblocks)

@@ -178,6 +178,7 @@ k_dense_gemv(int n, const double* __restrict__ a, const double* __restrict__ b,
 void dense_apply(const DenseInv& D, const double* b, double* x, const int* done)
 {
     if (D.n == 0) return;
+    ProfScope prof(100, D.n, (long long)D.n * D.n, 8.0 * D.n * D.n + 16.0 * D.n);
     FC_LAUNCH(k_dense_gemv, (D.n + 7) / 8, 256, 0, D.n, D.ainv, b, x, done);
 }
 

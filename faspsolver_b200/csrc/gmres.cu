@@ -339,7 +339,7 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
         FC_CUDA(cudaMemcpyAsync(st, &h0, sizeof(h0), cudaMemcpyHostToDevice, c.stream));
         red_partials((size_t)c.sm_count * 8);
         const int  g         = ggrid(n);
-        const bool use_graph = c.opt.graph && pc.capturable();
+        const bool use_graph = c.opt.graph && !c.opt.profile && pc.capturable();
         auto       pvec      = [&](int k) { return P + (size_t)k * ldp; };
 
         FC_CUDA(cudaEventRecord(t0, c.stream));

@@ -392,7 +392,7 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
             FC_LAUNCH(k_pcg_end, 1, 1, 0, st);
         };
 
-        const bool use_graph = c.opt.graph && pc.capturable();
+        const bool use_graph = c.opt.graph && !c.opt.profile && pc.capturable();
         int  launched = 0;
         bool finished = false;
         for (int it = 1; it <= MaxIt && !finished; ++it) {

@@ -101,6 +101,7 @@ double solver_stat(const fasp_cuda_solver_s* s, int what)
         case 2: return s->stats.ms;
         case 3: return (double)s->stats.launches;
         case 4: return s->ms_total;
+        case 5: return s->amg ? (double)s->amg->bytes : 0.0;
         default: return -1.0;
     }
 }

@@ -144,9 +144,11 @@ csr_rowblock_kernel(const CsrView A, const CsrArgs a, const int strict, double* 
         __syncthreads();
 
         // ---- phase 2: rows
+        // lanes per row: 1 while rows average <= 32 nonzeros (exact CPU order), then one
+        // lane per ~32 nonzeros as far as the CTA has threads for it
         int lpr = 1;
         if (!strict)
-            while (lpr < 32 && nrows * lpr * 2 <= TPB) lpr <<= 1;
+            while (lpr < 32 && nrows * lpr * 2 <= TPB && n > 32 * lpr * nrows) lpr <<= 1;
 
         if (lpr == 1) {
             if (tid < nrows) {
@@ -259,6 +261,11 @@ static void launch_mode(const DevCSR& A, const CsrView& v, const CsrArgs& a)
 void csr_launch(const DevCSR& A, const CsrArgs& a)
 {
     if (A.rows == 0) return;
+    const bool reads_y = (a.mode == CSR_AXPY || a.mode == CSR_RESID || a.mode >= CSR_JACOBI);
+    double     pbytes  = csr_spmv_bytes(A, reads_y);
+    if (a.mode == CSR_JACOBI || a.mode == CSR_L1) pbytes += 16.0 * A.rows;   // + u read, d read
+    if (a.mode >= CSR_POLY1) pbytes += 16.0 * A.rows;
+    ProfScope  prof(a.mode, A.rows, A.nnz, pbytes);
     CsrView v{A.ia, A.ja, A.val, A.rowblk, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap};
     switch (a.mode) {
         case CSR_MXV: launch_mode<CSR_MXV>(A, v, a); break;

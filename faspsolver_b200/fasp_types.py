@@ -125,6 +125,17 @@ class AMG_data_bsr(C.Structure):
                 ("P_nk", C.c_void_p), ("R_nk", C.c_void_p), ("w", dvector), ("mumps", Mumps_data)]
 
 
+class precond_data(C.Structure):
+    _fields_ = [("AMG_type", SHORT), ("print_level", SHORT), ("maxit", INT), ("max_levels", SHORT),
+                ("tol", REAL), ("cycle_type", SHORT), ("smoother", SHORT), ("smooth_order", SHORT),
+                ("presmooth_iter", SHORT), ("postsmooth_iter", SHORT), ("relaxation", REAL),
+                ("polynomial_degree", SHORT), ("coarsening_type", SHORT), ("coarse_solver", SHORT),
+                ("coarse_scaling", SHORT), ("amli_degree", SHORT), ("nl_amli_krylov_type", SHORT),
+                ("tentative_smooth", REAL), ("amli_coef", PREAL), ("mgl_data", C.POINTER(AMG_data)),
+                ("LU", C.c_void_p), ("A", C.POINTER(dCSRmat)), ("A_nk", C.c_void_p),
+                ("P_nk", C.c_void_p), ("R_nk", C.c_void_p), ("r", dvector), ("w", PREAL)]
+
+
 PRECOND_FCT = C.CFUNCTYPE(None, PREAL, PREAL, C.c_void_p)
 
 
@@ -156,7 +167,8 @@ class CSR:
 
     def to_scipy(self):
         import scipy.sparse as sp
-        return sp.csr_matrix((self.val, self.ja, self.ia), shape=self.shape)
+        # copies: scipy sorts indices / merges duplicates IN PLACE on some operations
+        return sp.csr_matrix((self.val.copy(), self.ja.copy(), self.ia.copy()), shape=self.shape)
 
     @staticmethod
     def from_scipy(m):
@@ -196,7 +208,7 @@ class BSR:
 
     def to_scipy(self):
         import scipy.sparse as sp
-        return sp.bsr_matrix((self.val.reshape(-1, self.nb, self.nb), self.ja, self.ia),
+        return sp.bsr_matrix((self.val.reshape(-1, self.nb, self.nb).copy(), self.ja.copy(), self.ia.copy()),
                              shape=(self.ROW * self.nb, self.COL * self.nb))
 
 

@@ -66,6 +66,11 @@ INT fasp_cuda_init(int device);
 long long fasp_cuda_launch_count(void);
 void      fasp_cuda_launch_count_reset(void);
 
+/* With option "profile" = 1 every matrix kernel is bracketed by CUDA events (graphs off);
+ * this returns the records gathered since the last call as text lines
+ * "<kind> <rows> <nnz> <ms> <algorithmic bytes>" and clears them. */
+long long fasp_cuda_profile_dump(char* buf, long long cap);
+
 /* Options that have no slot in FASP's parameter structs (ABI stays unchanged):
  *   "strict"       0/1  every CSR row summed left-to-right without FMA (bit-identical to
  *                       the sequential CPU loops, slower on long rows)           default 0

@@ -40,3 +40,10 @@ build_one () {  # $1 = name, $2 = extra flags, $3 = "patch" or ""
 
 if [ ! -f "$OUT/libfasp_seq.so" ] || [ "${1:-}" = "--force" ]; then build_one seq "" ""; fi
 if [ ! -f "$OUT/libfasp_omp.so" ] || [ "${1:-}" = "--force" ]; then build_one omp "-fopenmp" patch; fi
+
+# reference-arm bench driver (our code, reference headers + libfasp_omp.so)
+if [ ! -f "$OUT/fasp_ref_bench" ] || [ "$HERE/ref_bench.c" -nt "$OUT/fasp_ref_bench" ] || [ "${1:-}" = "--force" ]; then
+  gcc -O2 -std=gnu99 -fopenmp -w $INC "$HERE/ref_bench.c" -o "$OUT/fasp_ref_bench" \
+      -L"$OUT" -lfasp_omp -lm -Wl,-rpath,'$ORIGIN'
+  echo "built $OUT/fasp_ref_bench"
+fi

@@ -102,7 +102,8 @@ def test_golden_vectors(gpu, data, golden_vectors):
     A, g = data["FE"], golden_vectors
     y = np.empty(A.shape[0])
     assert gpu.fasp_cuda_blas_dcsr_mxv(A.ptr(), T.as_preal(np.ascontiguousarray(g["x"])), T.as_preal(y)) == 0
-    assert np.array_equal(y, g["mxv"])
+    assert np.array_equal(y, g["mxv"]), (int(np.sum(y != g["mxv"])), float(np.abs(y - g["mxv"]).max()),
+                                         np.nonzero(y != g["mxv"])[0][:10])
     y = data["FE_b"].copy()
     assert gpu.fasp_cuda_blas_dcsr_aAxpy(-1.0, A.ptr(), T.as_preal(np.ascontiguousarray(g["x"])), T.as_preal(y)) == 0
     assert np.array_equal(y, g["aAxpy_m1"])
