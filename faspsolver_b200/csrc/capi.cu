@@ -155,6 +155,11 @@ static int* option_slot(const char* key)
     if (!strcmp(key, "zero_guess")) return &o.zero_guess;
     if (!strcmp(key, "lookahead")) return &o.lookahead;
     if (!strcmp(key, "profile")) return &o.profile;
+    if (!strcmp(key, "vec_min_avg")) return &o.vec_min_avg;
+    if (!strcmp(key, "pipe")) return &o.pipe;
+    if (!strcmp(key, "pipe_ctas")) return &o.pipe_ctas;
+    if (!strcmp(key, "pipe_stages")) return &o.pipe_stages;
+    if (!strcmp(key, "pipe_tpb")) return &o.pipe_tpb;
     return nullptr;
 }
 INT fasp_cuda_set_option(const char* key, double value)

@@ -54,6 +54,11 @@ struct Options {
     int    graph            = 1;
     int    zero_guess       = 1;
     int    lookahead        = 2;   // Krylov iterations enqueued ahead of the status read
+    int    vec_min_avg      = 12;  // rows averaging >= this many nonzeros use the vector kernel
+    int    pipe             = 1;   // stream kernel: persistent TMA-pipelined variant
+    int    pipe_ctas        = 8;   // its CTAs per SM (upper bound)
+    int    pipe_stages      = 2;   // its shared-memory stages per CTA
+    int    pipe_tpb         = 128; // its threads per CTA = max rows per row block (64/128/256)
     int    profile          = 0;   // record CUDA events around every matrix kernel (no graphs)
 };
 
@@ -124,8 +129,11 @@ struct DevCSR {
     int*      ja   = nullptr;
     double*   val  = nullptr;
     int*      rowblk  = nullptr;
+    int2*     blkdesc = nullptr;  // {first row, ia[first row]} per row-block boundary
     int       nblk    = 0;
     int       blk_cap = 0;        // shared-memory products per CTA (entries)
+    int       blk_tpb = 256;      // rows per block bound = threads of the pipelined kernel
+    int       vec_lpr = 0;        // > 0: vector kernel with this many lanes per row
     double*   diag = nullptr;
     int*      dpos = nullptr;
     double*   l1   = nullptr;
@@ -191,6 +199,7 @@ struct CsrArgs {
     double        k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0;
     Reduce        red;
     const int*    done = nullptr;
+    bool          conditional = false;   // launch gated by a rarely-taken branch flag (profiling tag)
 };
 void csr_launch(const DevCSR& A, const CsrArgs& a);
 

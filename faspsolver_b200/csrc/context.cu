@@ -51,8 +51,8 @@ void ensure_init()
     c.sm_count = p.multiProcessorCount;
     c.l2_bytes = (size_t)p.l2CacheSize;
     FC_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    c.red_ticket = dalloc<unsigned int>(4);
-    FC_CUDA(cudaMemset(c.red_ticket, 0, 4 * sizeof(unsigned int)));
+    c.red_ticket = dalloc<unsigned int>((size_t)1 << 20);   // [0] groups done, [1+g] arrivals in group g
+    FC_CUDA(cudaMemset(c.red_ticket, 0, sizeof(unsigned int) << 20));
     c.inited = true;
     if (const char* s = getenv("FASP_CUDA_STRICT")) c.opt.strict = atoi(s);
     if (const char* s = getenv("FASP_CUDA_GRAPH")) c.opt.graph = atoi(s);
@@ -99,7 +99,8 @@ ProfScope::~ProfScope()
 double* red_partials(size_t nblocks)
 {
     Ctx&   c    = ctx();
-    size_t need = 4 * nblocks + 16;   // up to 4 sums per CTA
+    size_t need = 4 * (nblocks + nblocks / 256 + 2) + 16;   // up to 4 sums per CTA + per group
+    if (nblocks / 256 + 2 > ((size_t)1 << 20)) fail(ERROR_MAT_SIZE, "grid too large for the reduction tickets");
     if (need > c.red_cap) {
         if (c.capturing)
             fail(ERROR_SOLVER_MISC, "reduction scratch must be reserved before graph capture");

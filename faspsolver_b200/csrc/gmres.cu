@@ -381,7 +381,7 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
             FC_LAUNCH(k_gm_after_update, 1, 1, 0, st);
             Reduce red;
             red.nrm2_out = &st->rr;
-            A.apply(CSR_RESID, 1.0, x, b, r, red, &st->skip_true);
+            A.apply(CSR_RESID, 1.0, x, b, r, red, &st->skip_true, true);
             if (StopType == STOP_MOD_REL_RES) {
                 Reduce rx;
                 rx.nrm2_out = &st->xx;

@@ -378,10 +378,10 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
             FC_LAUNCH(k_pcg_stag_check, 1, 1, 0, st);
             Reduce rr;
             rr.nrm2_out = &st->rr;
-            A.apply(CSR_RESID, 1.0, u, b, r, rr, &st->skip_stag2);
+            A.apply(CSR_RESID, 1.0, u, b, r, rr, &st->skip_stag2, true);
             FC_LAUNCH(k_pcg_stag_check2, 1, 1, 0, st);
             // false-convergence guard: true residual
-            A.apply(CSR_RESID, 1.0, u, b, r, rr, &st->skip_cand);
+            A.apply(CSR_RESID, 1.0, u, b, r, rr, &st->skip_cand, true);
             FC_LAUNCH(k_pcg_cand_check, 1, 1, 0, st);
             // z = B r, zr = (z,r)
             Reduce rz;

@@ -11,15 +11,16 @@ struct LinOp {
     virtual ~LinOp() {}
     // mode: CSR_MXV / CSR_AXPY / CSR_RESID semantics
     virtual void apply(int mode, double alpha, const double* x, const double* b, double* y,
-                       const Reduce& red, const int* done) = 0;
+                       const Reduce& red, const int* done, bool conditional = false) = 0;
 };
 struct CsrOp : LinOp {
     const DevCSR* A;
     explicit CsrOp(const DevCSR* a) : A(a) { n = a->rows; }
     void apply(int mode, double alpha, const double* x, const double* b, double* y,
-               const Reduce& red, const int* done) override
+               const Reduce& red, const int* done, bool conditional = false) override
     {
         CsrArgs a;
+        a.conditional = conditional;
         a.mode  = mode;
         a.alpha = alpha;
         a.x     = x;

@@ -23,13 +23,15 @@
 
 namespace fc {
 
-constexpr int TPB = 256;
+constexpr int TPB     = 256;
+constexpr int CAP_MAX = 2048;   // largest row-block capacity (products per CTA)
 
 struct CsrView {
     const int*    ia;
     const int*    ja;
     const double* val;
     const int*    rowblk;
+    const int2*   blkdesc;
     const double* diag;
     const int*    dpos;
     const double* l1;
@@ -109,15 +111,34 @@ template <int MODE> struct ModeTraits {
     static constexpr bool skipdiag = (MODE == CSR_JACOBI);
 };
 
+// 16-byte asynchronous global->shared copy (LDGSTS), L2-only caching: the streamed matrix
+// slice goes straight to shared memory without occupying registers, so a CTA has its whole
+// slice in flight at once (memory-level parallelism independent of the register budget)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------
+// kernel S ("stream"): one CTA per row block, products parked in shared memory
+// ------------------------------------------------------------------------------------
 template <int MODE, bool PATTERN>
 __global__ void __launch_bounds__(TPB)
 csr_rowblock_kernel(const CsrView A, const CsrArgs a, const int strict, double* partials,
                     unsigned int* ticket)
 {
-    extern __shared__ double s_prod[];
-    __shared__ double        s_red[2][TPB / 32];
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ double s_red[2][TPB / 32];
 
     if (a.done != nullptr && *a.done != 0) return;
+
+    double* s_prod = reinterpret_cast<double*>(s_raw);              // cap + 8 entries
+    int*    s_ja   = reinterpret_cast<int*>(s_prod + A.cap + 8);    // cap + 8 entries
 
     const int tid   = threadIdx.x;
     const int r0    = A.rowblk[blockIdx.x];
@@ -132,14 +153,42 @@ csr_rowblock_kernel(const CsrView A, const CsrArgs a, const int strict, double* 
     const bool want_n2  = a.red.nrm2_out != nullptr;
 
     if (n <= A.cap) {
-        // ---- phase 1: stream the block's nonzeros, park val*x in shared memory
-        const int*    __restrict__ ja  = A.ja + k0;
-        const double* __restrict__ val = PATTERN ? nullptr : A.val + k0;
-#pragma unroll 4
-        for (int k = tid; k < n; k += TPB) {
-            const int    c  = ld_stream_i32(ja + k);
-            const double xv = __ldg(x + c);
-            s_prod[k]       = PATTERN ? xv : __dmul_rn(ld_stream_f64(val + k), xv);
+        // ---- phase 1a: asynchronous bulk staging of the block's ja / val slice. The slice is
+        // widened to 4-entry (16 B / 32 B) boundaries; the arrays are padded by 8 entries.
+        const int k0a = k0 & ~3;
+        const int d   = k0 - k0a;
+        const int na  = ((k0 + n + 3) & ~3) - k0a;
+        {
+            const int* gja = A.ja + k0a;
+            for (int c = tid; c < (na >> 2); c += TPB) cp_async16(s_ja + 4 * c, gja + 4 * c);
+            if (!PATTERN) {
+                const double* gval = A.val + k0a;
+                for (int c = tid; c < (na >> 1); c += TPB) cp_async16(s_prod + 2 * c, gval + 2 * c);
+            }
+            cp_async_wait_all();
+        }
+        __syncthreads();
+        // ---- phase 1b: gather x and form the products in place
+        double*    sp = s_prod + d;
+        const int* sj = s_ja + d;
+        // (indices first, then all gathers, then the products: a store to shared memory
+        // between two gathers would serialise them on the L2 latency)
+        {
+            constexpr int EPT = CAP_MAX / TPB;   // entries per thread, cap <= CAP_MAX
+            int           col[EPT];
+            double        xv[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int k = tid + e * TPB;
+                col[e]      = (k < n) ? sj[k] : -1;
+            }
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) xv[e] = (col[e] >= 0) ? __ldg(x + col[e]) : 0.0;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int k = tid + e * TPB;
+                if (k < n) sp[k] = PATTERN ? xv[e] : __dmul_rn(sp[k], xv[e]);
+            }
         }
         __syncthreads();
 
@@ -160,10 +209,10 @@ csr_rowblock_kernel(const CsrView A, const CsrArgs a, const int strict, double* 
                     acc            = a.b[row];
                     const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
                     for (int k = ka; k < kb; ++k)
-                        if (k != skip) acc = __dsub_rn(acc, s_prod[k]);
+                        if (k != skip) acc = __dsub_rn(acc, sp[k]);
                 } else {
                     acc = 0.0;
-                    for (int k = ka; k < kb; ++k) acc = __dadd_rn(acc, s_prod[k]);
+                    for (int k = ka; k < kb; ++k) acc = __dadd_rn(acc, sp[k]);
                 }
                 const double out = row_epilogue<MODE>(A, a, row, acc, true);
                 if (want_dot) red_dot = out * a.red.dot_with[row];
@@ -181,7 +230,7 @@ csr_rowblock_kernel(const CsrView A, const CsrArgs a, const int strict, double* 
                 const int kb   = A.ia[row + 1] - k0;
                 const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
                 for (int k = ka + gl; k < kb; k += lpr)
-                    if (k != skip) part += s_prod[k];
+                    if (k != skip) part += sp[k];
             }
             for (int off = lpr >> 1; off > 0; off >>= 1)
                 part += __shfl_xor_sync(0xffffffffu, part, off);
@@ -209,10 +258,11 @@ csr_rowblock_kernel(const CsrView A, const CsrArgs a, const int strict, double* 
             }
         } else {
             double part = 0.0;
+#pragma unroll 4
             for (int k = k0 + tid; k < k0 + n; k += TPB) {
-                if (k == skip) continue;
                 const double xv = __ldg(x + ld_stream_i32(A.ja + k));
-                part += PATTERN ? xv : ld_stream_f64(A.val + k) * xv;
+                const double p  = PATTERN ? xv : ld_stream_f64(A.val + k) * xv;
+                if (k != skip) part += p;
             }
             for (int off = 16; off > 0; off >>= 1)
                 part += __shfl_xor_sync(0xffffffffu, part, off);
@@ -239,23 +289,400 @@ csr_rowblock_kernel(const CsrView A, const CsrArgs a, const int strict, double* 
     }
 }
 
-template <int MODE>
-static void launch_mode(const DevCSR& A, const CsrView& v, const CsrArgs& a)
+// ------------------------------------------------------------------------------------
+// kernel P ("pipelined stream"): persistent CTAs, TMA bulk copies (cp.async.bulk +
+// mbarrier) stage the ja / val / ia slices of the NEXT row blocks into a ring of shared-
+// memory stages while the current block is gathered and reduced. The streamed bytes in
+// flight per SM are (stages - 1) x slice x CTAs/SM, independent of registers and occupancy;
+// the only latency left on a block's critical path is the x gather (L1/L2).
+// Same per-row arithmetic as kernel S (one thread per short row: exact CPU order).
+// ------------------------------------------------------------------------------------
+constexpr int P_MAX_STAGES = 8;
+constexpr int P_EPT = 8;            // entries per thread and stage: cap <= P_EPT * threads
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p)
 {
-    Ctx&          c    = ctx();
-    const size_t  smem = (size_t)A.blk_cap * sizeof(double);
+    return (unsigned int)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity)
+{
+    unsigned int ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes,
+                                         unsigned long long* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+struct PipeMeta {
+    int r0, nrows, k0, n;
+};
+
+template <int MODE, bool PATTERN, int T>
+__global__ void __launch_bounds__(T)
+csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nstages,
+                const int strict, double* partials, unsigned int* ticket)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ __align__(8) unsigned long long s_bar[P_MAX_STAGES];
+    __shared__ PipeMeta s_meta[P_MAX_STAGES];
+    __shared__ double   s_red[T / 32];
+    constexpr int EPT = P_EPT;   // cap <= P_EPT * T
+
+    if (a.done != nullptr && *a.done != 0) return;
+
+    const int    tid         = threadIdx.x;
+    const int    cap         = A.cap;
+    const int    G           = gridDim.x;
+    const size_t stage_bytes = ((size_t)(cap + 8) * 12 + (size_t)(T + 8) * 4 + 127) & ~(size_t)127;
+    auto st_val = [&](int s) { return reinterpret_cast<double*>(s_raw + (size_t)s * stage_bytes); };
+    auto st_ja  = [&](int s) { return reinterpret_cast<int*>(st_val(s) + cap + 8); };
+    auto st_ia  = [&](int s) { return st_ja(s) + cap + 8; };
+    const int2* __restrict__ desc = A.blkdesc;   // desc[b] = {first row, ia[first row]}
+    const double* __restrict__ x  = a.x;
+
+    // thread 0 is the producer: one mbarrier arrival (+ the bulk-copy byte count) per stage use
+    auto issue = [&](int blk, int s) {
+        const int2 d0 = desc[blk], d1 = desc[blk + 1];
+        PipeMeta   m{d0.x, d1.x - d0.x, d0.y, d1.y - d0.y};
+        s_meta[s] = m;
+        if (m.n <= cap) {
+            const int          k0a = m.k0 & ~3;
+            const unsigned int na  = (unsigned int)(((m.k0 + m.n + 3) & ~3) - k0a);
+            const int          r0a = m.r0 & ~3;
+            const unsigned int nra = (unsigned int)(((m.r0 + m.nrows + 1 + 3) & ~3) - r0a);
+            mbar_expect_tx(&s_bar[s], na * 4u + (PATTERN ? 0u : na * 8u) + nra * 4u);
+            if (na) bulk_g2s(st_ja(s), A.ja + k0a, na * 4u, &s_bar[s]);
+            if (!PATTERN && na) bulk_g2s(st_val(s), A.val + k0a, na * 8u, &s_bar[s]);
+            bulk_g2s(st_ia(s), A.ia + r0a, nra * 4u, &s_bar[s]);
+        } else {
+            mbar_expect_tx(&s_bar[s], 0u);   // long row: handled from global memory
+        }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < nstages; ++s) mbar_init(&s_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < nstages; ++s) {
+            const long long blk = (long long)blockIdx.x + (long long)s * G;
+            if (blk < nblk) issue((int)blk, s);
+        }
+    }
+    __syncthreads();
+
+    double     red_dot = 0.0, red_n2 = 0.0;
+    const bool want_dot = a.red.dot_out != nullptr;
+    const bool want_n2  = a.red.nrm2_out != nullptr;
+
+    int s = 0, ph = 0;   // stage of the current block and the parity of its ring round
+    for (long long blk = blockIdx.x; blk < nblk; blk += G) {
+        mbar_wait(&s_bar[s], (unsigned int)ph);
+        const PipeMeta m = s_meta[s];
+        const int r0 = m.r0, nrows = m.nrows, k0 = m.k0, n = m.n;
+        if (n <= cap) {
+            double*    sp  = st_val(s) + (k0 & 3);
+            const int* sj  = st_ja(s) + (k0 & 3);
+            const int* sia = st_ia(s) + (r0 & 3);   // sia[i] = ia[r0 + i]
+            int lpr = 1;
+            if (!strict)
+                while (lpr < 32 && nrows * lpr * 2 <= T && n > 32 * lpr * nrows) lpr <<= 1;
+            if (lpr == 1) {
+                // ---- one thread per row, straight from the staged slice: for a fixed position
+                // in the row the lanes of a warp gather x at neighbouring columns (consecutive
+                // rows of a stencil-like matrix), so the gathers coalesce into few sectors; the
+                // products are added left to right with separate roundings = the CPU loop.
+                if (tid < nrows) {
+                    const int row  = r0 + tid;
+                    const int ka   = sia[tid] - k0;
+                    const int kb   = sia[tid + 1] - k0;
+                    const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
+                    double    acc  = ModeTraits<MODE>::smoother ? a.b[row] : 0.0;
+                    constexpr int U = 8;
+                    for (int kk = ka; kk < kb; kk += U) {
+                        int    col[U];
+                        double xv[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) col[u] = (kk + u < kb) ? sj[kk + u] : -1;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) xv[u] = (col[u] >= 0) ? __ldg(x + col[u]) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int k = kk + u;
+                            if (k < kb && k != skip) {
+                                const double p = PATTERN ? xv[u] : __dmul_rn(sp[k], xv[u]);
+                                acc = ModeTraits<MODE>::smoother ? __dsub_rn(acc, p) : __dadd_rn(acc, p);
+                            }
+                        }
+                    }
+                    const double out = row_epilogue<MODE>(A, a, row, acc, true);
+                    if (want_dot) red_dot += out * a.red.dot_with[row];
+                    if (want_n2) red_n2 += out * out;
+                }
+            } else {
+                // ---- longer rows: entry-wise gather, products parked in the stage, then a
+                // group of lpr lanes per row adds them
+                {
+                    int    col[EPT];
+                    double xv[EPT];
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) {
+                        const int k = tid + e * T;
+                        col[e]      = (k < n) ? sj[k] : -1;
+                    }
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) xv[e] = (col[e] >= 0) ? __ldg(x + col[e]) : 0.0;
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) {
+                        const int k = tid + e * T;
+                        if (k < n) sp[k] = PATTERN ? xv[e] : __dmul_rn(sp[k], xv[e]);
+                    }
+                }
+                __syncthreads();
+                const int  g     = tid / lpr;
+                const int  gl    = tid - g * lpr;
+                const bool valid = g < nrows;
+                double     part  = 0.0;
+                int        row   = r0;
+                if (valid) {
+                    row            = r0 + g;
+                    const int ka   = sia[g] - k0;
+                    const int kb   = sia[g + 1] - k0;
+                    const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
+                    for (int k = ka + gl; k < kb; k += lpr)
+                        if (k != skip) part += sp[k];
+                }
+                for (int off = lpr >> 1; off > 0; off >>= 1)
+                    part += __shfl_xor_sync(0xffffffffu, part, off);
+                if (valid && gl == 0) {
+                    const double out = row_epilogue<MODE>(A, a, row, part, false);
+                    if (want_dot) red_dot += out * a.red.dot_with[row];
+                    if (want_n2) red_n2 += out * out;
+                }
+            }
+        } else {
+            // ---- one row longer than a stage: whole CTA on it, straight from global memory
+            const int row  = r0;
+            const int skip = ModeTraits<MODE>::skipdiag ? k0 + A.dpos[row] : -1;
+            double    part = 0.0;
+            if (strict) {
+                if (tid == 0) {
+                    double acc = ModeTraits<MODE>::smoother ? a.b[row] : 0.0;
+                    for (int k = k0; k < k0 + n; ++k) {
+                        if (k == skip) continue;
+                        const double p = PATTERN ? x[A.ja[k]] : __dmul_rn(A.val[k], x[A.ja[k]]);
+                        acc = ModeTraits<MODE>::smoother ? __dsub_rn(acc, p) : __dadd_rn(acc, p);
+                    }
+                    const double out = row_epilogue<MODE>(A, a, row, acc, true);
+                    if (want_dot) red_dot += out * a.red.dot_with[row];
+                    if (want_n2) red_n2 += out * out;
+                }
+            } else {
+#pragma unroll 4
+                for (int k = k0 + tid; k < k0 + n; k += T) {
+                    const double xk = __ldg(x + ld_stream_i32(A.ja + k));
+                    const double p  = PATTERN ? xk : ld_stream_f64(A.val + k) * xk;
+                    if (k != skip) part += p;
+                }
+                for (int off = 16; off > 0; off >>= 1)
+                    part += __shfl_xor_sync(0xffffffffu, part, off);
+                if ((tid & 31) == 0) s_red[tid >> 5] = part;
+                __syncthreads();
+                if (tid == 0) {
+                    double acc = 0.0;
+                    for (int w = 0; w < T / 32; ++w) acc += s_red[w];
+                    const double out = row_epilogue<MODE>(A, a, row, acc, false);
+                    if (want_dot) red_dot += out * a.red.dot_with[row];
+                    if (want_n2) red_n2 += out * out;
+                }
+            }
+        }
+        __syncthreads();   // stage s fully consumed
+        if (tid == 0) {
+            const long long refill = blk + (long long)nstages * G;
+            if (refill < nblk) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue((int)refill, s);
+            }
+        }
+        if (++s == nstages) s = 0, ph ^= 1;
+    }
+
+    if (want_dot || want_n2) {
+        double v[2] = {red_dot, red_n2};
+        grid_reduce<2, 0>(v, partials, ticket, [&](const double* t) {
+            if (want_dot) *a.red.dot_out = t[0];
+            if (want_n2) *a.red.nrm2_out = t[1];
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// kernel V ("vector"): LPR lanes per row, no shared memory (the whole L1 serves the x
+// gathers). Used for rows that average more than ~12 nonzeros: the coarse levels of a
+// classical-AMG hierarchy (19 ... 1400 nonzeros per row). Lanes of a group read consecutive
+// entries (coalesced), partial sums are combined with warp shuffles.
+// ------------------------------------------------------------------------------------
+template <int MODE, bool PATTERN, int LPR>
+__global__ void __launch_bounds__(TPB)
+csr_vector_kernel(const CsrView A, const CsrArgs a, const int nrows, double* partials,
+                  unsigned int* ticket)
+{
+    if (a.done != nullptr && *a.done != 0) return;
+    const long long gt   = (long long)blockIdx.x * TPB + threadIdx.x;
+    const int       lane = (int)(gt & (LPR - 1));
+    const long long rowl = gt / LPR;
+    const bool      valid = rowl < nrows;
+    const int       row   = valid ? (int)rowl : 0;
+    const double* __restrict__ x   = a.x;
+    const int*    __restrict__ ja  = A.ja;
+    const double* __restrict__ val = A.val;
+    double part = 0.0;
+    if (valid) {
+        const int ka   = A.ia[row];
+        const int kb   = A.ia[row + 1];
+        const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
+        // U predicated loads per lane are issued together (indices, values, then gathers):
+        // a plain unrolled loop would fall into its serial remainder for short trip counts
+        constexpr int U = 4;
+        for (int kk = ka + lane; kk < kb; kk += U * LPR) {
+            int    col[U];
+            double v[U], xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = kk + u * LPR;
+                col[u]      = (k < kb) ? ld_stream_i32(ja + k) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = kk + u * LPR;
+                v[u]        = (PATTERN || k >= kb) ? 1.0 : ld_stream_f64(val + k);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = (col[u] >= 0) ? __ldg(x + col[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = kk + u * LPR;
+                if (k != skip) part += v[u] * xv[u];
+            }
+        }
+    }
+#pragma unroll
+    for (int off = LPR >> 1; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    double red_dot = 0.0, red_n2 = 0.0;
+    const bool want_dot = a.red.dot_out != nullptr;
+    const bool want_n2  = a.red.nrm2_out != nullptr;
+    if (valid && lane == 0) {
+        const double out = row_epilogue<MODE>(A, a, row, part, false);
+        if (want_dot) red_dot = out * a.red.dot_with[row];
+        if (want_n2) red_n2 = out * out;
+    }
+    if (want_dot || want_n2) {
+        double v[2] = {red_dot, red_n2};
+        grid_reduce<2, 0>(v, partials, ticket, [&](const double* t) {
+            if (want_dot) *a.red.dot_out = t[0];
+            if (want_n2) *a.red.nrm2_out = t[1];
+        });
+    }
+}
+
+template <int MODE, bool PATTERN, int LPR>
+static void launch_vector(const DevCSR& A, const CsrView& v, const CsrArgs& a)
+{
+    const long long threads = (long long)A.rows * LPR;
+    const int       grid    = (int)((threads + TPB - 1) / TPB);
+    double*         part    = nullptr;
+    unsigned int*   tick    = nullptr;
+    if (a.red.dot_out || a.red.nrm2_out) {
+        part = red_partials((size_t)grid);
+        tick = red_ticket();
+    }
+    FC_LAUNCH((csr_vector_kernel<MODE, PATTERN, LPR>), grid, TPB, 0, v, a, A.rows, part, tick);
+}
+
+// persistent grid: as many CTAs per SM as the stage rings allow
+template <int MODE, bool PATTERN, int T>
+static void launch_pipe(const DevCSR& A, const CsrView& v, const CsrArgs& a, double* part,
+                        unsigned int* tick)
+{
+    Ctx&         c     = ctx();
+    const size_t stage = ((size_t)(A.blk_cap + 8) * 12 + (size_t)(T + 8) * 4 + 127) & ~(size_t)127;
+    int          nst   = c.opt.pipe_stages;
+    if (nst < 2) nst = 2;
+    if (nst > P_MAX_STAGES) nst = P_MAX_STAGES;
+    const size_t smem = stage * nst;
+    static bool  attr_set = false;
+    if (!attr_set) {
+        FC_CUDA(cudaFuncSetAttribute(csr_pipe_kernel<MODE, PATTERN, T>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    int per_sm = (int)((size_t)(226 * 1024) / (smem + 2048));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > c.opt.pipe_ctas) per_sm = c.opt.pipe_ctas;
+    if (per_sm > 2048 / T) per_sm = 2048 / T;
+    long long grid = (long long)c.sm_count * per_sm;
+    if (grid > A.nblk) grid = A.nblk;
+    FC_LAUNCH((csr_pipe_kernel<MODE, PATTERN, T>), (int)grid, T, smem, v, a, A.nblk, nst,
+              c.opt.strict, part, tick);
+}
+
+template <int MODE, bool PATTERN>
+static void launch_pattern(const DevCSR& A, const CsrView& v, const CsrArgs& a)
+{
+    Ctx& c = ctx();
+    if (A.vec_lpr > 0 && !c.opt.strict) {
+        switch (A.vec_lpr) {
+            case 4: launch_vector<MODE, PATTERN, 4>(A, v, a); return;
+            case 8: launch_vector<MODE, PATTERN, 8>(A, v, a); return;
+            case 16: launch_vector<MODE, PATTERN, 16>(A, v, a); return;
+            default: launch_vector<MODE, PATTERN, 32>(A, v, a); return;
+        }
+    }
     double*       part = nullptr;
     unsigned int* tick = nullptr;
     if (a.red.dot_out || a.red.nrm2_out) {
         part = red_partials((size_t)A.nblk);
         tick = red_ticket();
     }
-    if (A.val == nullptr)
-        FC_LAUNCH((csr_rowblock_kernel<MODE, true>), A.nblk, TPB, smem, v, a, c.opt.strict, part,
-                  tick);
-    else
-        FC_LAUNCH((csr_rowblock_kernel<MODE, false>), A.nblk, TPB, smem, v, a, c.opt.strict,
-                  part, tick);
+    if (c.opt.pipe) {
+        switch (A.blk_tpb) {
+            case 64: launch_pipe<MODE, PATTERN, 64>(A, v, a, part, tick); return;
+            case 128: launch_pipe<MODE, PATTERN, 128>(A, v, a, part, tick); return;
+            default: launch_pipe<MODE, PATTERN, 256>(A, v, a, part, tick); return;
+        }
+    }
+    const size_t smem = (size_t)(A.blk_cap + 8) * (sizeof(double) + sizeof(int));
+    FC_LAUNCH((csr_rowblock_kernel<MODE, PATTERN>), A.nblk, TPB, smem, v, a, c.opt.strict, part, tick);
+}
+
+template <int MODE>
+static void launch_mode(const DevCSR& A, const CsrView& v, const CsrArgs& a)
+{
+    if (A.val == nullptr) launch_pattern<MODE, true>(A, v, a);
+    else launch_pattern<MODE, false>(A, v, a);
 }
 
 void csr_launch(const DevCSR& A, const CsrArgs& a)
@@ -265,8 +692,8 @@ void csr_launch(const DevCSR& A, const CsrArgs& a)
     double     pbytes  = csr_spmv_bytes(A, reads_y);
     if (a.mode == CSR_JACOBI || a.mode == CSR_L1) pbytes += 16.0 * A.rows;   // + u read, d read
     if (a.mode >= CSR_POLY1) pbytes += 16.0 * A.rows;
-    ProfScope  prof(a.mode, A.rows, A.nnz, pbytes);
-    CsrView v{A.ia, A.ja, A.val, A.rowblk, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap};
+    ProfScope  prof(a.conditional ? a.mode + 50 : a.mode, A.rows, A.nnz, pbytes);
+    CsrView v{A.ia, A.ja, A.val, A.rowblk, A.blkdesc, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap};
     switch (a.mode) {
         case CSR_MXV: launch_mode<CSR_MXV>(A, v, a); break;
         case CSR_AXPY: launch_mode<CSR_AXPY>(A, v, a); break;
@@ -355,7 +782,7 @@ __global__ void rowmax_kernel(int rows, const double* l1, const double* dinv, do
     if (threadIdx.x == 0) blockmax[blockIdx.x] = s[0];
 }
 
-static void build_rowblocks(int rows, const int* ia, int cap, std::vector<int>& rb)
+static void build_rowblocks(int rows, const int* ia, int cap, int maxrows, std::vector<int>& rb)
 {
     rb.clear();
     rb.reserve((size_t)rows / 128 + 2);
@@ -364,7 +791,7 @@ static void build_rowblocks(int rows, const int* ia, int cap, std::vector<int>& 
         rb.push_back(r);
         const long long base = ia[r];
         int             e    = r + 1;   // a block always takes its first row, however long
-        while (e < rows && e - r < TPB && (long long)ia[e + 1] - base <= cap) ++e;
+        while (e < rows && e - r < maxrows && (long long)ia[e + 1] - base <= cap) ++e;
         r = e;
     }
     rb.push_back(rows);
@@ -381,7 +808,8 @@ void csr_upload(DevCSR& d, int rows, int cols, long long nnz, const int* ia, con
     d.nnz  = nnz;
     if (nnz >= 2147483647LL) fail(ERROR_MAT_SIZE, "csr_upload: nnz exceeds 32-bit offsets");
     const size_t pad = 8;
-    d.ia             = dalloc<int>((size_t)rows + 1);
+    d.ia             = dalloc<int>((size_t)rows + 1 + pad);
+    FC_CUDA(cudaMemsetAsync(d.ia + rows + 1, 0, sizeof(int) * pad, c.stream));
     d.ja             = dalloc<int>((size_t)nnz + pad);
     FC_CUDA(cudaMemcpyAsync(d.ia, ia, sizeof(int) * ((size_t)rows + 1), cudaMemcpyHostToDevice,
                             c.stream));
@@ -396,19 +824,34 @@ void csr_upload(DevCSR& d, int rows, int cols, long long nnz, const int* ia, con
         FC_CUDA(cudaMemsetAsync(d.val + nnz, 0, sizeof(double) * pad, c.stream));
         d.bytes += sizeof(double) * ((size_t)nnz + pad);
     }
-    // row blocks: capacity ~ 256 average rows, between 1024 and 4096 products per CTA
+    // row blocks: at most T rows (T = threads of the pipelined kernel) and cap products, cap ~ T
+    // average rows and <= 8 T (12 B of shared memory per product and stage)
     const double avg = rows > 0 ? (double)nnz / rows : 1.0;
-    long long    cap = (long long)(avg * TPB + 255) / 256 * 256;
-    if (cap < 1024) cap = 1024;
-    if (cap > 4096) cap = 4096;
+    int T = c.opt.pipe_tpb;
+    if (T != 64 && T != 128 && T != 256) T = 128;
+    d.blk_tpb     = T;
+    long long cap = (long long)(avg * T + 63) / 64 * 64;
+    if (cap < 4 * T) cap = 4 * T;
+    if (cap > P_EPT * T) cap = P_EPT * T;
     d.blk_cap = (int)cap;
+    // kernel choice: short rows -> stream kernel (exact CPU summation order); longer rows ->
+    // vector kernel with LPR lanes per row
+    d.vec_lpr = 0;
+    const int vmin = c.opt.vec_min_avg;
+    if (vmin > 0 && avg >= vmin) d.vec_lpr = avg < 2.0 * vmin ? 8 : (avg < 4.0 * vmin ? 16 : 32);
     std::vector<int> rb;
-    build_rowblocks(rows, ia, d.blk_cap, rb);
+    build_rowblocks(rows, ia, d.blk_cap, d.blk_tpb, rb);
     d.nblk   = (int)rb.size() - 1;
     d.rowblk = dalloc<int>(rb.size());
     FC_CUDA(cudaMemcpyAsync(d.rowblk, rb.data(), sizeof(int) * rb.size(), cudaMemcpyHostToDevice,
                             c.stream));
     d.bytes += sizeof(int) * rb.size();
+    std::vector<int2> bd(rb.size());
+    for (size_t i = 0; i < rb.size(); ++i) bd[i] = make_int2(rb[i], ia[rb[i]]);
+    d.blkdesc = dalloc<int2>(bd.size());
+    FC_CUDA(cudaMemcpyAsync(d.blkdesc, bd.data(), sizeof(int2) * bd.size(), cudaMemcpyHostToDevice,
+                            c.stream));
+    d.bytes += sizeof(int2) * bd.size();
     FC_CUDA(cudaStreamSynchronize(c.stream));   // host staging vectors go out of scope
     red_partials((size_t)d.nblk);
 }
@@ -419,6 +862,7 @@ void csr_free(DevCSR& d)
     dfree(d.ja);
     dfree(d.val);
     dfree(d.rowblk);
+    dfree(d.blkdesc);
     dfree(d.diag);
     dfree(d.dpos);
     dfree(d.l1);

@@ -49,7 +49,7 @@ def test_mxv_matches_reference(gpu, ref, data):
 def test_mxv_short_rows_bit_exact(gpu, ref, data):
     """Rows reduced by a single thread follow the CPU order and rounding exactly."""
     rng = np.random.default_rng(12)
-    for name, A in (("FE", data["FE"]), ("p7_24", PB.poisson7(24)), ("p27_12", PB.poisson27(12))):
+    for name, A in (("FE", data["FE"]), ("p7_24", PB.poisson7(24)), ("cd7_16", PB.convdiff7(16))):
         x = rng.uniform(-1, 1, A.shape[1])
         y = np.empty(A.shape[0])
         assert gpu.fasp_cuda_blas_dcsr_mxv(A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
