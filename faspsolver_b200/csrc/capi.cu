@@ -160,6 +160,8 @@ static int* option_slot(const char* key)
     if (!strcmp(key, "pipe_ctas")) return &o.pipe_ctas;
     if (!strcmp(key, "pipe_stages")) return &o.pipe_stages;
     if (!strcmp(key, "pipe_tpb")) return &o.pipe_tpb;
+    if (!strcmp(key, "rowwise_max")) return &o.rowwise_max;
+    if (!strcmp(key, "vec_lpr")) return &o.vec_lpr;
     return nullptr;
 }
 INT fasp_cuda_set_option(const char* key, double value)
@@ -170,6 +172,7 @@ INT fasp_cuda_set_option(const char* key, double value)
         return ERROR_INPUT_PAR;
     }
     *s = (int)value;
+    ctx().opt_epoch++;
     return FASP_SUCCESS;
 }
 double fasp_cuda_get_option(const char* key)

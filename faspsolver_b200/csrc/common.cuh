@@ -54,11 +54,13 @@ struct Options {
     int    graph            = 1;
     int    zero_guess       = 1;
     int    lookahead        = 2;   // Krylov iterations enqueued ahead of the status read
-    int    vec_min_avg      = 12;  // rows averaging >= this many nonzeros use the vector kernel
+    int    vec_min_avg      = 24;  // rows averaging >= this many nonzeros use the vector kernel
     int    pipe             = 1;   // stream kernel: persistent TMA-pipelined variant
     int    pipe_ctas        = 8;   // its CTAs per SM (upper bound)
     int    pipe_stages      = 2;   // its shared-memory stages per CTA
     int    pipe_tpb         = 128; // its threads per CTA = max rows per row block (64/128/256)
+    int    rowwise_max      = 32;  // blocks averaging <= this many nonzeros per row: one thread per row
+    int    vec_lpr          = 0;   // > 0: force this many lanes per row in the vector kernel
     int    profile          = 0;   // record CUDA events around every matrix kernel (no graphs)
 };
 
@@ -72,6 +74,7 @@ struct Ctx {
     bool         capturing = false;     // inside a stream capture: launches counted per replay
     long long    captured  = 0;
     Options      opt;
+    long long    opt_epoch = 0;     // bumped by every set_option: invalidates captured graphs
     // scratch for grid reductions (partials + ticket), grown on demand
     double*       red_partials = nullptr;
     size_t        red_cap      = 0;

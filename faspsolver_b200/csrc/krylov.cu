@@ -289,13 +289,28 @@ static int vgrid(size_t n)
     return (int)g;
 }
 
-struct PinnedStatus {
-    int    done, iter, status, converged;
-    double relres;
-};
+PcgCache::~PcgCache() { release(); }
+void PcgCache::release()
+{
+    g_init.reset();
+    g_iter.reset();
+    for (auto& e : ev) cudaEventDestroy(e);
+    ev.clear();
+    if (t0) cudaEventDestroy(t0);
+    if (t1) cudaEventDestroy(t1);
+    t0 = t1 = nullptr;
+    if (pin) cudaFreeHost(pin);
+    pin = nullptr;
+    dfree(work);
+    dfree(st);
+    work = nullptr;
+    st   = nullptr;
+    n    = 0;
+    hcap = 0;
+}
 
 int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double abstol,
-              int MaxIt, int StopType, int PrtLvl, SolveStats* stats)
+              int MaxIt, int StopType, int PrtLvl, SolveStats* stats, PcgCache* cache)
 {
     ensure_init();
     Ctx&         c = ctx();
@@ -306,32 +321,41 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
              StopType);
     if (PrtLvl > PRINT_NONE) printf("\nCalling CG solver (CSR) ...\n");
 
+    PcgCache  local;
+    PcgCache& W = cache ? *cache : local;
     const long long launches0 = c.launches;
     const int       hcap      = MaxIt + 2;
-    double*   work = dalloc<double>(4 * n + 3 * (size_t)hcap);
+    const int       look      = c.opt.lookahead < 1 ? 1 : c.opt.lookahead;
+    // (re)build the workspace when the shape changes; graphs are tied to the buffers
+    if (W.n != n || W.hcap != hcap || W.look != look) {
+        W.release();
+        W.work = dalloc<double>(4 * n + 3 * (size_t)hcap);
+        W.st   = static_cast<void*>(dalloc<PcgState>(1));
+        FC_CUDA(cudaMallocHost(&W.pin, sizeof(int) * 4 * (look + 1)));
+        W.ev.resize(look + 1);
+        for (auto& e : W.ev) FC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        FC_CUDA(cudaEventCreate(&W.t0));
+        FC_CUDA(cudaEventCreate(&W.t1));
+        W.n = n, W.hcap = hcap, W.look = look;
+    }
+    // graphs bake in pointers and kernel choices: re-capture when any of them changed
+    if (W.kA != A.key() || W.kb != b || W.ku != u || W.kpc != pc.key() || W.kstop != StopType ||
+        W.kepoch != c.opt_epoch) {
+        W.g_init.reset();
+        W.g_iter.reset();
+        W.kA = A.key(), W.kb = b, W.ku = u, W.kpc = pc.key(), W.kstop = StopType;
+        W.kepoch = c.opt_epoch;
+    }
+    double *  work = W.work;
     double *  p = work, *z = p + n, *r = z + n, *t = r + n;
     double *  hr = t + n, *ha = hr + hcap, *hf = ha + hcap;
-    PcgState* st = dalloc<PcgState>(1);
-    PinnedStatus* pin = nullptr;
-    const int     look = c.opt.lookahead < 1 ? 1 : c.opt.lookahead;
-    FC_CUDA(cudaMallocHost(&pin, sizeof(PinnedStatus) * (look + 1)));
-    std::vector<cudaEvent_t> ev(look + 1);
-    for (auto& e : ev) FC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    cudaEvent_t t0, t1;
-    FC_CUDA(cudaEventCreate(&t0));
-    FC_CUDA(cudaEventCreate(&t1));
-    CapturedGraph   graph;
-    int             ret = 0;
+    PcgState* st  = static_cast<PcgState*>(W.st);
+    int*      pin = W.pin;
+    std::vector<cudaEvent_t>& ev = W.ev;
+    cudaEvent_t t0 = W.t0, t1 = W.t1;
+    int         ret = 0;
 
-    auto cleanup = [&]() {
-        graph.reset();
-        for (auto& e : ev) cudaEventDestroy(e);
-        cudaEventDestroy(t0);
-        cudaEventDestroy(t1);
-        cudaFreeHost(pin);
-        dfree(work);
-        dfree(st);
-    };
+    auto cleanup = [&]() {};
 
     try {
         PcgState h0;
@@ -346,10 +370,11 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
         red_partials((size_t)c.sm_count * 8);
         const int* done = &st->done;
         const int  g    = vgrid(n);
+        const bool use_graph = c.opt.graph && !c.opt.profile && pc.capturable();
 
         FC_CUDA(cudaEventRecord(t0, c.stream));
         // r = b - A u ; z = B r ; p = z ; temp1 = (z,r)
-        {
+        auto initial = [&]() {
             Reduce red;
             red.nrm2_out = &st->rr;
             A.apply(CSR_RESID, 1.0, u, b, r, red, nullptr);
@@ -364,7 +389,8 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
             pc.apply(r, z, rz, nullptr);
             FC_LAUNCH(k_pcg_init, 1, 1, 0, st, hr, ha, hf);
             vec_copy(p, z, n, done);
-        }
+        };
+        W.g_init.run(use_graph, initial);
 
         auto iteration = [&]() {
             Reduce rt;   // t = A p, tp = (t,p)
@@ -392,24 +418,19 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
             FC_LAUNCH(k_pcg_end, 1, 1, 0, st);
         };
 
-        const bool use_graph = c.opt.graph && !c.opt.profile && pc.capturable();
-        int  launched = 0;
         bool finished = false;
         for (int it = 1; it <= MaxIt && !finished; ++it) {
-            graph.run(use_graph, iteration);
-            launched          = it;
-            const int slot    = it % (look + 1);
-            // status snapshot: {done, iter, status, converged} are contiguous ints
-            FC_CUDA(cudaMemcpyAsync(&pin[slot].done, &st->done, sizeof(int),
-                                    cudaMemcpyDeviceToHost, c.stream));
+            W.g_iter.run(use_graph, iteration);
+            const int slot = it % (look + 1);
+            FC_CUDA(cudaMemcpyAsync(&pin[4 * slot], &st->done, sizeof(int), cudaMemcpyDeviceToHost,
+                                    c.stream));
             FC_CUDA(cudaEventRecord(ev[slot], c.stream));
             if (it > look) {
                 const int old = (it - look) % (look + 1);
                 FC_CUDA(cudaEventSynchronize(ev[old]));
-                if (pin[old].done) finished = true;
+                if (pin[4 * old]) finished = true;
             }
         }
-        (void)launched;
         FC_CUDA(cudaEventRecord(t1, c.stream));
         FC_CUDA(cudaStreamSynchronize(c.stream));
 

@@ -9,6 +9,7 @@ namespace fc {
 struct LinOp {
     int n = 0;
     virtual ~LinOp() {}
+    virtual const void* key() const { return this; }   // identity of the resident operator
     // mode: CSR_MXV / CSR_AXPY / CSR_RESID semantics
     virtual void apply(int mode, double alpha, const double* x, const double* b, double* y,
                        const Reduce& red, const int* done, bool conditional = false) = 0;
@@ -16,6 +17,7 @@ struct LinOp {
 struct CsrOp : LinOp {
     const DevCSR* A;
     explicit CsrOp(const DevCSR* a) : A(a) { n = a->rows; }
+    const void* key() const override { return A; }
     void apply(int mode, double alpha, const double* x, const double* b, double* y,
                const Reduce& red, const int* done, bool conditional = false) override
     {
@@ -35,6 +37,7 @@ struct CsrOp : LinOp {
 // z = B r on device vectors
 struct Prec {
     virtual ~Prec() {}
+    virtual const void* key() const { return this; }
     virtual void apply(const double* r, double* z, const Reduce& red, const int* done) = 0;
     virtual bool capturable() const { return true; }
 };
@@ -50,6 +53,7 @@ struct IdentityPrec : Prec {
 struct AmgPrec : Prec {
     Amg* h;
     explicit AmgPrec(Amg* h_) : h(h_) {}
+    const void* key() const override { return h; }
     void apply(const double* r, double* z, const Reduce& red, const int* done) override
     {
         amg_apply(*h, r, z, red, done);
@@ -74,9 +78,28 @@ struct SolveStats {
     std::vector<double> hist_relres, hist_absres, hist_factor;
 };
 
+// Workspace + captured graphs of a PCG solve, reusable across solves on the same operator,
+// preconditioner and vectors (a solver object keeps one: no allocation, capture or
+// instantiation on the repeated-solve path).
+struct PcgCache {
+    double* work = nullptr;
+    void*   st   = nullptr;
+    int*    pin  = nullptr;
+    size_t  n    = 0;
+    int     hcap = 0, look = 0;
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t   t0 = nullptr, t1 = nullptr;
+    CapturedGraph g_init, g_iter;
+    const void *  kA = nullptr, *kb = nullptr, *ku = nullptr, *kpc = nullptr;
+    int           kstop = 0;
+    long long     kepoch = -1;
+    ~PcgCache();
+    void release();
+};
+
 // All vectors are device pointers. Returns FASP status (>=0 iterations, <0 ERROR_*).
 int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double abstol,
-              int MaxIt, int StopType, int PrtLvl, SolveStats* stats);
+              int MaxIt, int StopType, int PrtLvl, SolveStats* stats, PcgCache* cache = nullptr);
 // restart > 0; variable == true -> Baker/Jessup/Kolev restart adaptation (KryPvgmres.c)
 int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, double abstol,
                 int MaxIt, int restart, int StopType, int PrtLvl, bool variable,

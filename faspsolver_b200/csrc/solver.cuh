@@ -8,6 +8,7 @@
 struct fasp_cuda_solver_s {
     fc::Amg*       amg  = nullptr;     // CSR hierarchy (level-0 A doubles as the Krylov operator)
     fc::SolveStats stats;
+    fc::PcgCache   pcg_cache;      // workspace + graphs reused across solves
     double         ms_total = 0.0;     // last solve incl. H2D/D2H
     double*        d_b = nullptr;      // staging vectors for host-pointer solves
     double*        d_x = nullptr;

@@ -37,6 +37,7 @@ struct CsrView {
     const double* l1;
     const double* dinv;
     int           cap;
+    int           rowwise_max;
 };
 
 __device__ __forceinline__ int ld_stream_i32(const int* p)
@@ -408,7 +409,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
             const int* sia = st_ia(s) + (r0 & 3);   // sia[i] = ia[r0 + i]
             int lpr = 1;
             if (!strict)
-                while (lpr < 32 && nrows * lpr * 2 <= T && n > 32 * lpr * nrows) lpr <<= 1;
+                while (lpr < 32 && nrows * lpr * 2 <= T && n > A.rowwise_max * lpr * nrows) lpr <<= 1;
             if (lpr == 1) {
                 // ---- one thread per row, straight from the staged slice: for a fixed position
                 // in the row the lanes of a warp gather x at neighbouring columns (consecutive
@@ -693,7 +694,7 @@ void csr_launch(const DevCSR& A, const CsrArgs& a)
     if (a.mode == CSR_JACOBI || a.mode == CSR_L1) pbytes += 16.0 * A.rows;   // + u read, d read
     if (a.mode >= CSR_POLY1) pbytes += 16.0 * A.rows;
     ProfScope  prof(a.conditional ? a.mode + 50 : a.mode, A.rows, A.nnz, pbytes);
-    CsrView v{A.ia, A.ja, A.val, A.rowblk, A.blkdesc, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap};
+    CsrView v{A.ia, A.ja, A.val, A.rowblk, A.blkdesc, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap, ctx().opt.rowwise_max};
     switch (a.mode) {
         case CSR_MXV: launch_mode<CSR_MXV>(A, v, a); break;
         case CSR_AXPY: launch_mode<CSR_AXPY>(A, v, a); break;
@@ -838,7 +839,7 @@ void csr_upload(DevCSR& d, int rows, int cols, long long nnz, const int* ia, con
     // vector kernel with LPR lanes per row
     d.vec_lpr = 0;
     const int vmin = c.opt.vec_min_avg;
-    if (vmin > 0 && avg >= vmin) d.vec_lpr = avg < 2.0 * vmin ? 8 : (avg < 4.0 * vmin ? 16 : 32);
+    if (vmin > 0 && avg >= vmin) d.vec_lpr = c.opt.vec_lpr > 0 ? c.opt.vec_lpr : (avg < 96 ? 8 : (avg < 384 ? 16 : 32));
     std::vector<int> rb;
     build_rowblocks(rows, ia, d.blk_cap, d.blk_tpb, rb);
     d.nblk   = (int)rb.size() - 1;

@@ -21,10 +21,10 @@ for r in data:
             i = hdr.index(w)
             print("%-70s %s %s" % (w, r[i][:90], units[i]))
     for i, h in enumerate(hdr):
-        if 'issue_stalled' in h and h.endswith('per_warp_active.pct'):
+        if 'average_warps_issue_stalled' in h and h.endswith('per_issue_active.ratio'):
             try:
                 v = float(r[i])
             except ValueError:
                 continue
-            if v > 4:
-                print("%-70s %.1f" % (h.replace('smsp__warp_issue_stalled_', 'stall:'), v))
+            if v > 0.5:
+                print("%-70s %.2f" % (h.replace('smsp__average_warps_issue_stalled_', 'stall:').replace('_per_issue_active.ratio', ''), v))
