@@ -1,6 +1,7 @@
 // amg.cuh — device-resident AMG hierarchy and multigrid cycle (CSR and BSR).
 #pragma once
 #include "common.cuh"
+#include "bsr.cuh"
 
 namespace fc {
 
@@ -11,6 +12,7 @@ struct DenseInv {
 };
 void dense_invert_csr(DenseInv& D, const DevCSR& A);       // Gauss-Jordan, partial pivoting
 void dense_invert_host(DenseInv& D, int n, const std::vector<double>& a_rowmajor);
+void dense_invert_bsr(DenseInv& D, const DevBSR& A);          // expanded to (ROW nb)^2
 void dense_apply(const DenseInv& D, const double* b, double* x, const int* done);
 void dense_free(DenseInv& D);
 
@@ -59,5 +61,31 @@ void amg_apply(Amg& h, const double* r, double* z, const Reduce& red, const int*
 // used by fasp_cuda_solver_mgcycle and the AMG-as-solver loop (PreMGSolve.c:49).
 void amg_cycle_inplace(Amg& h, const double* b, double* x, bool x_is_zero, const Reduce& red,
                        const int* done);
+
+// ---- BSR twin (PreMGCycle.c:287-566, PreBSR.c:1149) ----
+struct BLevel {
+    DevBSR  A, P, R;
+    int     n = 0;            // ROW * nb
+    double* b = nullptr;
+    double* xa = nullptr;
+    double* xb = nullptr;
+    double* w = nullptr;
+    double* diaginv = nullptr;   // ROW * nb*nb inverted diagonal blocks
+};
+struct BAmg {
+    std::vector<BLevel> lv;
+    int    nl = 0, nb = 1;
+    short  smoother = SMOOTHER_JACOBI, cycle_type = V_CYCLE, presmooth = 1, postsmooth = 1;
+    short  coarse_scaling = OFF;
+    double relax = 1.0, tol = 1e-6;
+    int    maxit = 1;
+    DenseInv coarse;
+    size_t bytes = 0;
+};
+BAmg* bamg_upload(AMG_data_bsr* mgl, AMG_param* param);
+void  bamg_free(BAmg* h);
+void  bamg_apply(BAmg& h, const double* r, double* z, const Reduce& red, const int* done);
+void  bamg_cycle_inplace(BAmg& h, const double* b, double* x, bool x_is_zero, const Reduce& red,
+                         const int* done);
 
 } // namespace fc

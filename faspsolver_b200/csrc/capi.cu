@@ -891,3 +891,296 @@ INT fasp_cuda_amg_solve(AMG_data* mgl, AMG_param* param)
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------------------------------
+// BSR twins
+// ------------------------------------------------------------------------------------
+struct fasp_cuda_bsr_s {
+    DevBSR m;
+};
+struct fasp_cuda_bamg_s {
+    BAmg* h;
+};
+
+namespace {
+void check_bsr(const dBSRmat* A)
+{
+    if (!A || A->ROW < 0 || A->COL < 0 || A->NNZ < 0 || !A->IA || (A->NNZ > 0 && (!A->JA || !A->val)))
+        fail(ERROR_DATA_STRUCTURE, "invalid dBSRmat");
+    if (A->storage_manner != 0) fail(ERROR_INPUT_PAR, "dBSRmat: only row-major blocks (storage_manner 0)");
+}
+struct TmpBSR {
+    DevBSR m;
+    explicit TmpBSR(const dBSRmat* A)
+    {
+        check_bsr(A);
+        bsr_upload(m, A->ROW, A->COL, A->NNZ, A->nb, A->IA, A->JA, A->val);
+    }
+    ~TmpBSR() { bsr_free(m); }
+};
+int host_bsr_spmv(const dBSRmat* A, int mode, double alpha, const double* x, double* y)
+{
+    ensure_init();
+    TmpBSR dA(A);
+    const size_t nx = (size_t)A->COL * A->nb, ny = (size_t)A->ROW * A->nb;
+    DVec   dx(x, nx), dy(ny);
+    if (mode == BSR_AXPY)
+        FC_CUDA(cudaMemcpyAsync(dy.p, y, sizeof(double) * ny, cudaMemcpyHostToDevice, ctx().stream));
+    BsrArgs a;
+    a.mode  = mode;
+    a.alpha = alpha;
+    a.x     = dx.p;
+    a.y     = dy.p;
+    bsr_launch(dA.m, a);
+    dy.to_host(y);
+    return FASP_SUCCESS;
+}
+int bsr_krylov_host(dBSRmat* A, dvector* b, dvector* x, precond* pc, double tol, double abstol, int MaxIt,
+                    int restart, int StopType, int PrtLvl, int which)
+{
+    ensure_init();
+    TmpBSR       dA(A);
+    BsrOp        op(&dA.m);
+    const size_t n = b->row;
+    DVec         db(b->val, n), dx(x->val, n);
+    PrecChoice   pch;
+    if (pc == nullptr) pch.p = new IdentityPrec(n);
+    else pch.p = new HostPrec(pc, n);
+    int ret;
+    if (which == 0) ret = pcg_solve(op, db.p, dx.p, *pch.p, tol, abstol, MaxIt, StopType, PrtLvl, nullptr);
+    else ret = gmres_solve(op, db.p, dx.p, *pch.p, tol, abstol, MaxIt, restart, StopType, PrtLvl, which == 2, nullptr);
+    dx.to_host(x->val);
+    return ret;
+}
+} // namespace
+
+extern "C" {
+
+INT fasp_cuda_blas_dbsr_mxv(const dBSRmat* A, const REAL* x, REAL* y)
+{
+    API_TRY
+    return host_bsr_spmv(A, BSR_MXV, 1.0, x, y);
+    API_CATCH(code__)
+}
+INT fasp_cuda_blas_dbsr_aAxpy(const REAL alpha, const dBSRmat* A, const REAL* x, REAL* y)
+{
+    API_TRY
+    return host_bsr_spmv(A, BSR_AXPY, alpha, x, y);
+    API_CATCH(code__)
+}
+void fasp_cuda_blas_mxv_bsr(const void* A, const REAL* x, REAL* y)
+{
+    fasp_cuda_blas_dbsr_mxv(static_cast<const dBSRmat*>(A), x, y);
+}
+
+INT fasp_cuda_smoother_dbsr_jacobi1(dBSRmat* A, dvector* b, dvector* u, REAL* diaginv)
+{
+    API_TRY
+    ensure_init();
+    TmpBSR       dA(A);
+    const size_t n = (size_t)A->ROW * A->nb, nd = (size_t)A->ROW * A->nb * A->nb;
+    DVec         db(b->val, n), du(u->val, n), dv(n), dd(diaginv, nd);
+    BsrArgs      a;
+    a.mode = BSR_JACOBI, a.x = du.p, a.b = db.p, a.y = dv.p, a.diaginv = dd.p;
+    bsr_launch(dA.m, a);
+    dv.to_host(u->val);
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+
+fasp_cuda_bsr* fasp_cuda_dbsr_upload(const dBSRmat* A)
+{
+    API_TRY
+    ensure_init();
+    check_bsr(A);
+    fasp_cuda_bsr* d = new fasp_cuda_bsr_s();
+    try {
+        bsr_upload(d->m, A->ROW, A->COL, A->NNZ, A->nb, A->IA, A->JA, A->val);
+    } catch (...) {
+        delete d;
+        throw;
+    }
+    return d;
+    API_CATCH(nullptr)
+}
+void fasp_cuda_dbsr_free(fasp_cuda_bsr* dA)
+{
+    if (!dA) return;
+    bsr_free(dA->m);
+    delete dA;
+}
+INT fasp_cuda_dbsr_spmv_dev(const fasp_cuda_bsr* dA, int mode, REAL alpha, const REAL* x, const REAL* b, REAL* y)
+{
+    API_TRY
+    if (!dA) fail(ERROR_INPUT_PAR, "null matrix handle");
+    if (mode < 0 || mode > 2) fail(ERROR_INPUT_PAR, "spmv mode must be 0, 1 or 2");
+    BsrArgs a;
+    a.mode = mode, a.alpha = alpha, a.x = x, a.b = b, a.y = y;
+    bsr_launch(dA->m, a);
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+double fasp_cuda_dbsr_time_kernel(const fasp_cuda_bsr* dA, int what, int warm, int reps, int flush)
+{
+    API_TRY
+    if (!dA) fail(ERROR_INPUT_PAR, "null matrix handle");
+    Ctx&          c  = ctx();
+    const DevBSR& m  = dA->m;
+    const size_t  nx = (size_t)(m.COL > m.ROW ? m.COL : m.ROW) * m.nb;
+    DVec          x(nx), y(nx), b(nx), dinv((size_t)m.ROW * m.nb * m.nb);
+    std::vector<double> hx(nx);
+    unsigned long long  sd = 88172645463325252ULL;
+    for (size_t i = 0; i < nx; ++i) {
+        sd ^= sd << 13, sd ^= sd >> 7, sd ^= sd << 17;
+        hx[i] = (double)(sd >> 11) / 9007199254740992.0 * 2.0 - 1.0;
+    }
+    FC_CUDA(cudaMemcpy(x.p, hx.data(), sizeof(double) * nx, cudaMemcpyHostToDevice));
+    FC_CUDA(cudaMemcpy(b.p, hx.data(), sizeof(double) * nx, cudaMemcpyHostToDevice));
+    FC_CUDA(cudaMemset(y.p, 0, sizeof(double) * nx));
+    FC_CUDA(cudaMemset(dinv.p, 0, sizeof(double) * dinv.n));
+    BsrArgs a;
+    a.x = x.p, a.b = b.p, a.y = y.p, a.diaginv = dinv.p;
+    switch (what) {
+        case 0: a.mode = BSR_MXV; break;
+        case 1: a.mode = BSR_AXPY, a.alpha = -1.0; break;
+        case 2: a.mode = BSR_RESID; break;
+        case 10: a.mode = BSR_JACOBI; break;
+        default: fail(ERROR_INPUT_PAR, "time_kernel: unknown kernel id %d", what);
+    }
+    cudaEvent_t e0, e1;
+    FC_CUDA(cudaEventCreate(&e0));
+    FC_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < warm; ++i) bsr_launch(m, a);
+    double total = 0.0;
+    for (int i = 0; i < reps; ++i) {
+        if (flush) flush_l2();
+        FC_CUDA(cudaEventRecord(e0, c.stream));
+        bsr_launch(m, a);
+        FC_CUDA(cudaEventRecord(e1, c.stream));
+        FC_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        FC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return total / (reps > 0 ? reps : 1);
+    API_CATCH(-1.0)
+}
+
+fasp_cuda_bamg* fasp_cuda_bamg_upload(AMG_data_bsr* mgl, AMG_param* param)
+{
+    API_TRY
+    BAmg*           h = bamg_upload(mgl, param);
+    fasp_cuda_bamg* r = new fasp_cuda_bamg_s();
+    r->h              = h;
+    return r;
+    API_CATCH(nullptr)
+}
+void fasp_cuda_bamg_free(fasp_cuda_bamg* h)
+{
+    if (!h) return;
+    bamg_free(h->h);
+    delete h;
+}
+
+INT fasp_cuda_solver_mgcycle_bsr(AMG_data_bsr* mgl, AMG_param* param)
+{
+    API_TRY
+    BAmg* h = bamg_upload(mgl, param);
+    try {
+        const size_t n = h->lv[0].n;
+        DVec         db(mgl[0].b.val, n), dx(mgl[0].x.val, n);
+        bamg_cycle_inplace(*h, db.p, dx.p, false, Reduce(), nullptr);
+        dx.to_host(mgl[0].x.val);
+    } catch (...) {
+        bamg_free(h);
+        throw;
+    }
+    bamg_free(h);
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+
+INT fasp_cuda_solver_dbsr_pcg(dBSRmat* A, dvector* b, dvector* u, precond* pc, const REAL tol, const REAL abstol,
+                              const INT MaxIt, const SHORT StopType, const SHORT PrtLvl)
+{
+    API_TRY
+    return bsr_krylov_host(A, b, u, pc, tol, abstol, MaxIt, 0, StopType, PrtLvl, 0);
+    API_CATCH(code__)
+}
+INT fasp_cuda_solver_dbsr_pgmres(dBSRmat* A, dvector* b, dvector* x, precond* pc, const REAL tol, const REAL abstol,
+                                 const INT MaxIt, const SHORT restart, const SHORT StopType, const SHORT PrtLvl)
+{
+    API_TRY
+    return bsr_krylov_host(A, b, x, pc, tol, abstol, MaxIt, restart, StopType, PrtLvl, 1);
+    API_CATCH(code__)
+}
+INT fasp_cuda_solver_dbsr_pvgmres(dBSRmat* A, dvector* b, dvector* x, precond* pc, const REAL tol, const REAL abstol,
+                                  const INT MaxIt, const SHORT restart, const SHORT StopType, const SHORT PrtLvl)
+{
+    API_TRY
+    return bsr_krylov_host(A, b, x, pc, tol, abstol, MaxIt, restart, StopType, PrtLvl, 2);
+    API_CATCH(code__)
+}
+INT fasp_cuda_solver_dbsr_itsolver(dBSRmat* A, dvector* b, dvector* x, precond* pc, ITS_param* itparam)
+{
+    // SolBSR.c:55-140
+    const SHORT prt = itparam->print_level, stop = itparam->stop_type;
+    const INT   maxit = itparam->maxit, restart = itparam->restart;
+    const REAL  tol = itparam->tol, abstol = itparam->abstol;
+    switch (itparam->itsolver_type) {
+        case SOLVER_CG: return fasp_cuda_solver_dbsr_pcg(A, b, x, pc, tol, abstol, maxit, stop, prt);
+        case SOLVER_GMRES: return fasp_cuda_solver_dbsr_pgmres(A, b, x, pc, tol, abstol, maxit, (SHORT)restart, stop, prt);
+        case SOLVER_VGMRES: return fasp_cuda_solver_dbsr_pvgmres(A, b, x, pc, tol, abstol, maxit, (SHORT)restart, stop, prt);
+        default:
+            set_last_error("itsolver_type not on the device path (supported: CG 1, GMRES 4, VGMRES 5)");
+            return ERROR_SOLVER_TYPE;
+    }
+}
+
+fasp_cuda_solver* fasp_cuda_krylov_bamg_create(AMG_data_bsr* mgl, AMG_param* amgparam)
+{
+    API_TRY
+    return solver_create_bsr(mgl, amgparam);
+    API_CATCH(nullptr)
+}
+
+INT fasp_cuda_solver_dbsr_krylov_amg(dBSRmat* A, dvector* b, dvector* x, ITS_param* itparam, AMG_param* amgparam)
+{
+    API_TRY
+    ensure_init();
+    check_bsr(A);
+    require_host_fasp();
+    HostFasp& hf = host_fasp();
+    if (!hf.amg_data_bsr_create || !hf.amg_data_bsr_free || !hf.setup_ua_bsr || !hf.dbsr_create || !hf.dbsr_cp)
+        fail(ERROR_AMG_SETUP, "the host FASP library lacks the BSR AMG setup routines");
+    // SolBSR.c:371-390
+    AMG_data_bsr* mgl = hf.amg_data_bsr_create(amgparam->max_levels);
+    mgl[0].A          = hf.dbsr_create(A->ROW, A->COL, A->NNZ, A->nb, A->storage_manner);
+    mgl[0].b          = hf.dvec_create(mgl[0].A.ROW * mgl[0].A.nb);
+    mgl[0].x          = hf.dvec_create(mgl[0].A.COL * mgl[0].A.nb);
+    hf.dbsr_cp(A, &mgl[0].A);
+    INT st = (amgparam->AMG_type == SA_AMG && hf.setup_sa_bsr) ? hf.setup_sa_bsr(mgl, amgparam)
+                                                               : hf.setup_ua_bsr(mgl, amgparam);
+    if (st < 0) {
+        hf.amg_data_bsr_free(mgl, amgparam);
+        fail(ERROR_AMG_SETUP, "host BSR AMG setup failed with status %d", st);
+    }
+    fasp_cuda_solver* s = nullptr;
+    INT               ret;
+    try {
+        s   = solver_create_bsr(mgl, amgparam);
+        ret = solver_solve_host(s, b->val, x->val, itparam);
+    } catch (...) {
+        solver_destroy(s);
+        hf.amg_data_bsr_free(mgl, amgparam);
+        throw;
+    }
+    solver_destroy(s);
+    hf.amg_data_bsr_free(mgl, amgparam);
+    return ret;
+    API_CATCH(code__)
+}
+
+} // extern "C"

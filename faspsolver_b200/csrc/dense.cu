@@ -148,6 +148,18 @@ void dense_invert_csr(DenseInv& D, const DevCSR& A)
     gauss_jordan(n, D.ainv);
 }
 
+void dense_invert_bsr(DenseInv& D, const DevBSR& A)
+{
+    dense_free(D);
+    if (A.ROW != A.COL) fail(ERROR_MAT_SIZE, "coarsest BSR matrix is not square");
+    const int n = A.ROW * A.nb;
+    D.n         = n;
+    D.ainv      = dalloc<double>((size_t)n * n);
+    FC_CUDA(cudaMemsetAsync(D.ainv, 0, sizeof(double) * (size_t)n * n, ctx().stream));
+    bsr_to_dense(A, D.ainv);
+    gauss_jordan(n, D.ainv);
+}
+
 void dense_invert_host(DenseInv& D, int n, const std::vector<double>& a)
 {
     dense_free(D);

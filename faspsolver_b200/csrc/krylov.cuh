@@ -34,6 +34,26 @@ struct CsrOp : LinOp {
     }
 };
 
+struct BsrOp : LinOp {
+    const DevBSR* A;
+    explicit BsrOp(const DevBSR* a) : A(a) { n = a->ROW * a->nb; }
+    const void* key() const override { return A; }
+    void apply(int mode, double alpha, const double* x, const double* b, double* y,
+               const Reduce& red, const int* done, bool conditional = false) override
+    {
+        BsrArgs a;
+        a.conditional = conditional;
+        a.mode  = (mode == CSR_MXV) ? BSR_MXV : (mode == CSR_AXPY ? BSR_AXPY : BSR_RESID);
+        a.alpha = alpha;
+        a.x     = x;
+        a.b     = b;
+        a.y     = y;
+        a.red   = red;
+        a.done  = done;
+        bsr_launch(*A, a);
+    }
+};
+
 // z = B r on device vectors
 struct Prec {
     virtual ~Prec() {}
@@ -57,6 +77,15 @@ struct AmgPrec : Prec {
     void apply(const double* r, double* z, const Reduce& red, const int* done) override
     {
         amg_apply(*h, r, z, red, done);
+    }
+};
+struct BAmgPrec : Prec {
+    BAmg* h;
+    explicit BAmgPrec(BAmg* h_) : h(h_) {}
+    const void* key() const override { return h; }
+    void apply(const double* r, double* z, const Reduce& red, const int* done) override
+    {
+        bamg_apply(*h, r, z, red, done);
     }
 };
 // arbitrary host callback pc->fct(r, z, data) with host pointers: D2H r, call, H2D z

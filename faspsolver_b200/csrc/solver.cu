@@ -50,21 +50,39 @@ fasp_cuda_solver_s* solver_create_csr(AMG_data* mgl, AMG_param* amgparam)
     return s;
 }
 
+fasp_cuda_solver_s* solver_create_bsr(AMG_data_bsr* mgl, AMG_param* amgparam)
+{
+    ensure_init();
+    fasp_cuda_solver_s* s = new fasp_cuda_solver_s();
+    try {
+        AMG_param p = *amgparam;
+        p.tol       = 1e-6;   // fasp_precond_dbsr_amg re-initialises the parameters (PreBSR.c:1159-1169)
+        s->bamg     = bamg_upload(mgl, &p);
+        s->n        = (size_t)s->bamg->lv[0].n;
+        s->d_b      = dalloc<double>(s->n);
+        s->d_x      = dalloc<double>(s->n);
+        FC_CUDA(cudaMallocHost(&s->pin, sizeof(double) * 2 * s->n));
+    } catch (...) {
+        solver_destroy(s);
+        throw;
+    }
+    return s;
+}
+
 void solver_destroy(fasp_cuda_solver_s* s)
 {
     if (!s) return;
     amg_free(s->amg);
+    bamg_free(s->bamg);
     dfree(s->d_b);
     dfree(s->d_x);
     if (s->pin) cudaFreeHost(s->pin);
     delete s;
 }
 
-int solver_solve_dev(fasp_cuda_solver_s* s, const double* b_dev, double* x_dev, ITS_param* it)
+static int run_krylov(fasp_cuda_solver_s* s, LinOp& op, Prec& pc, const double* b_dev, double* x_dev,
+                      ITS_param* it)
 {
-    if (!s || !s->amg) fail(ERROR_INPUT_PAR, "null solver");
-    CsrOp   op(&s->amg->lv[0].A);
-    AmgPrec pc(s->amg);
     switch (it->itsolver_type) {
         case SOLVER_CG:
             return pcg_solve(op, b_dev, x_dev, pc, it->tol, it->abstol, it->maxit, it->stop_type,
@@ -82,9 +100,22 @@ int solver_solve_dev(fasp_cuda_solver_s* s, const double* b_dev, double* x_dev, 
     }
 }
 
+int solver_solve_dev(fasp_cuda_solver_s* s, const double* b_dev, double* x_dev, ITS_param* it)
+{
+    if (!s || (!s->amg && !s->bamg)) fail(ERROR_INPUT_PAR, "null solver");
+    if (s->amg) {
+        CsrOp   op(&s->amg->lv[0].A);
+        AmgPrec pc(s->amg);
+        return run_krylov(s, op, pc, b_dev, x_dev, it);
+    }
+    BsrOp    op(&s->bamg->lv[0].A);
+    BAmgPrec pc(s->bamg);
+    return run_krylov(s, op, pc, b_dev, x_dev, it);
+}
+
 int solver_solve_host(fasp_cuda_solver_s* s, const double* b, double* x, ITS_param* it)
 {
-    if (!s || !s->amg) fail(ERROR_INPUT_PAR, "null solver");
+    if (!s || (!s->amg && !s->bamg)) fail(ERROR_INPUT_PAR, "null solver");
     Ctx&         c  = ctx();
     const size_t n  = s->n;
     const auto   w0 = std::chrono::steady_clock::now();
@@ -111,7 +142,7 @@ double solver_stat(const fasp_cuda_solver_s* s, int what)
         case 2: return s->stats.ms;
         case 3: return (double)s->stats.launches;
         case 4: return s->ms_total;
-        case 5: return s->amg ? (double)s->amg->bytes : 0.0;
+        case 5: return s->amg ? (double)s->amg->bytes : (s->bamg ? (double)s->bamg->bytes : 0.0);
         default: return -1.0;
     }
 }

@@ -7,6 +7,7 @@
 
 struct fasp_cuda_solver_s {
     fc::Amg*       amg  = nullptr;     // CSR hierarchy (level-0 A doubles as the Krylov operator)
+    fc::BAmg*      bamg = nullptr;     // or a BSR hierarchy
     fc::SolveStats stats;
     fc::PcgCache   pcg_cache;      // workspace + graphs reused across solves
     double         ms_total = 0.0;     // last solve incl. H2D/D2H
@@ -48,6 +49,7 @@ HostFasp& host_fasp();
 void      require_host_fasp();
 
 fasp_cuda_solver_s* solver_create_csr(AMG_data* mgl, AMG_param* amgparam);
+fasp_cuda_solver_s* solver_create_bsr(AMG_data_bsr* mgl, AMG_param* amgparam);
 void                solver_destroy(fasp_cuda_solver_s* s);
 int    solver_solve_dev(fasp_cuda_solver_s* s, const double* b_dev, double* x_dev, ITS_param* it);
 int    solver_solve_host(fasp_cuda_solver_s* s, const double* b, double* x, ITS_param* it);

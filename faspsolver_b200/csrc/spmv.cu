@@ -20,6 +20,7 @@
 // A row longer than cap is its own block and is reduced by the whole CTA.
 #include "common.cuh"
 #include "reduce.cuh"
+#include "pipe.cuh"
 
 namespace fc {
 
@@ -300,42 +301,6 @@ csr_rowblock_kernel(const CsrView A, const CsrArgs a, const int strict, double* 
 // ------------------------------------------------------------------------------------
 constexpr int P_MAX_STAGES = 8;
 constexpr int P_EPT = 8;            // entries per thread and stage: cap <= P_EPT * threads
-
-__device__ __forceinline__ unsigned int smem_u32(const void* p)
-{
-    return (unsigned int)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity)
-{
-    unsigned int ok;
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            " selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes,
-                                         unsigned long long* bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
 
 struct PipeMeta {
     int r0, nrows, k0, n;

@@ -61,6 +61,7 @@ class RefFasp(HostFasp):
             "fasp_solver_dcsr_itsolver": (INT, [P(dCSRmat), P(dvector), P(dvector), P(precond), P(ITS_param)]),
             "fasp_precond_amg": (None, [PREAL, PREAL, C.c_void_p]),
             "fasp_param_amg_to_prec": (None, [C.c_void_p, P(AMG_param)]),
+            "fasp_dbsr_getdiaginv": (dvector, [P(dBSRmat)]),
             "fasp_solver_amg": (INT, [P(dCSRmat), P(dvector), P(dvector), P(AMG_param)]),
         }
         for name, (res, args) in sig.items():

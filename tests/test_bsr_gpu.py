@@ -1,0 +1,112 @@
+"""BSR path: block SpMV / aAxpy / block-Jacobi / BSR cycle / BSR AMG-Krylov vs the sequential
+reference on FASP's shipped SPE01 black-oil matrix and a synthetic 3x3-block 7-point system."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from faspsolver_b200 import api
+from faspsolver_b200 import fasp_types as T
+from faspsolver_b200 import problems as PB
+from faspsolver_b200.fasp_types import BSR
+
+pytestmark = pytest.mark.gpu
+
+
+def _mats(data):
+    rng = np.random.default_rng(5)
+    out = [("SPE01", data["SPE"]), ("blockoil_6", PB.blockoil7(6)[0])]
+    for nb in (1, 2, 4, 5, 7, 8):   # every block size the reference special-cases + generic
+        s = PB.poisson7(5, scaled=False)
+        val = rng.uniform(-1, 1, (s.nnz, nb, nb))
+        out.append(("rand_nb%d" % nb, BSR(s.shape[0], s.shape[1], nb, s.ia, s.ja, val)))
+    return out
+
+
+def test_bsr_mxv_bit_exact(gpu, ref, data):
+    rng = np.random.default_rng(31)
+    for name, A in _mats(data):
+        x = rng.uniform(-1, 1, A.COL * A.nb)
+        y, yr = np.empty(A.ROW * A.nb), np.empty(A.ROW * A.nb)
+        assert gpu.fasp_cuda_blas_dbsr_mxv(A.ptr(), T.as_preal(x), T.as_preal(y)) == 0, gpu.fasp_cuda_last_error()
+        ref.L.fasp_blas_dbsr_mxv(A.ptr(), T.as_preal(x), T.as_preal(yr))
+        assert np.array_equal(y, yr), (name, np.abs(y - yr).max())
+
+
+@pytest.mark.parametrize("alpha", [1.0, -1.0, 0.3])
+def test_bsr_aAxpy(gpu, ref, data, alpha):
+    rng = np.random.default_rng(32)
+    for name, A in _mats(data):
+        x = rng.uniform(-1, 1, A.COL * A.nb)
+        y0 = rng.uniform(-1, 1, A.ROW * A.nb)
+        y, yr = y0.copy(), y0.copy()
+        assert gpu.fasp_cuda_blas_dbsr_aAxpy(alpha, A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
+        ref.L.fasp_blas_dbsr_aAxpy(alpha, A.ptr(), T.as_preal(x), T.as_preal(yr))
+        assert np.array_equal(y, yr), (name, alpha, np.abs(y - yr).max())
+
+
+def test_bsr_jacobi1_bit_exact(gpu, ref, data):
+    rng = np.random.default_rng(33)
+    for name, A in _mats(data)[:4]:
+        n = A.ROW * A.nb
+        dinv = ref.L.fasp_dbsr_getdiaginv(A.ptr())
+        b, u0 = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+        u, ur = T.Vec(u0.copy()), T.Vec(u0.copy())
+        assert gpu.fasp_cuda_smoother_dbsr_jacobi1(A.ptr(), T.Vec(b).ptr(), u.ptr(), dinv.val) == 0
+        ref.L.fasp_smoother_dbsr_jacobi1(A.ptr(), T.Vec(b).ptr(), ur.ptr(), dinv.val)
+        assert np.array_equal(u.a, ur.a), (name, np.abs(u.a - ur.a).max())
+
+
+def _bsr_amg(ref, **kw):
+    return ref.amg_param(print_level=0, AMG_type=T.UA_AMG, aggregation_type=T.VMB,
+                         smoother=T.SMOOTHER_JACOBI, coarse_dof=100, **kw)
+
+
+def test_bsr_mgcycle_matches_reference(gpu, ref):
+    A, b = PB.blockoil7(10)
+    amg = _bsr_amg(ref)
+    mgl = ref.bamg_setup(A, amg)
+    try:
+        n = A.ROW * A.nb
+        assert mgl[0].num_levels >= 2
+        bv = np.ctypeslib.as_array(mgl[0].b.val, shape=(n,))
+        xv = np.ctypeslib.as_array(mgl[0].x.val, shape=(n,))
+        bv[:] = b
+        xv[:] = 0.0
+        ref.L.fasp_solver_mgcycle_bsr(mgl, C.byref(amg))
+        x_ref = xv.copy()
+        bv[:] = b
+        xv[:] = 0.0
+        assert gpu.fasp_cuda_solver_mgcycle_bsr(mgl, C.byref(amg)) == 0, gpu.fasp_cuda_last_error()
+        x_gpu = xv.copy()
+    finally:
+        ref.bamg_free(mgl, amg)
+    # the reference's coarsest solve is GMRES to param->tol = 1e-6 (PreMGCycle.c:443-459), ours direct
+    assert np.linalg.norm(x_gpu - x_ref) / np.linalg.norm(x_ref) < 1e-5
+
+
+def test_bsr_krylov_amg(gpu, ref):
+    """config 5 recipe at small size: 3x3-block 7-point, UA/VMB, block Jacobi, VGMRES(30), tol 1e-8."""
+    A, b = PB.blockoil7(12)
+    it = ref.its_param(itsolver_type=T.SOLVER_VGMRES, restart=30, tol=1e-8, maxit=500, print_level=0)
+    vb, vx, vxr = T.Vec(b), T.Vec(np.zeros_like(b)), T.Vec(np.zeros_like(b))
+    st_ref = ref.L.fasp_solver_dbsr_krylov_amg(A.ptr(), vb.ptr(), vxr.ptr(), C.byref(it), C.byref(_bsr_amg(ref)))
+    st = gpu.fasp_cuda_solver_dbsr_krylov_amg(A.ptr(), vb.ptr(), vx.ptr(), C.byref(it), C.byref(_bsr_amg(ref)))
+    assert st > 0, (st, gpu.fasp_cuda_last_error())
+    # exact coarse solve vs the reference's inexact inner GMRES: counts may differ slightly
+    assert st <= st_ref + 2, (st, st_ref)
+    S = A.to_scipy()
+    assert np.linalg.norm(b - S @ vx.a) / np.linalg.norm(b) <= 1e-8 * 1.001
+    assert np.linalg.norm(vx.a - vxr.a) / np.linalg.norm(vxr.a) < 1e-6
+
+
+def test_bsr_krylov_no_precond(gpu, ref, data):
+    """BSR-format Krylov with pc == NULL on SPE01 (reg.gcc pins CG/GMRES in BSR format)."""
+    A, b = data["SPE"], data["SPE_b"]
+    vb, vx, vxr = T.Vec(b), T.Vec(np.zeros_like(b)), T.Vec(np.zeros_like(b))
+    st = gpu.fasp_cuda_solver_dbsr_pvgmres(A.ptr(), vb.ptr(), vx.ptr(), None, 1e-6, 1e-18, 500, 30, 1, 0)
+    st_ref = ref.L.fasp_solver_dbsr_pvgmres(A.ptr(), vb.ptr(), vxr.ptr(), None, 1e-6, 1e-18, 500, 30, 1, 0)
+    assert (st > 0) == (st_ref > 0), (st, st_ref)
+    if st > 0:
+        assert abs(st - st_ref) <= 2
+        assert np.linalg.norm(vx.a - vxr.a) / np.linalg.norm(vxr.a) < 1e-5
