@@ -61,6 +61,7 @@ def lib():
         "fasp_cuda_smoother_dcsr_L1diag": (INT, [P(dvector), INT, INT, INT, P(dCSRmat), P(dvector), INT]),
         "fasp_cuda_smoother_dcsr_poly": (INT, [P(dCSRmat), P(dvector), P(dvector), INT, INT, INT]),
         "fasp_cuda_smoother_dcsr_gs_multicolor": (INT, [P(dvector), P(dCSRmat), P(dvector), INT, INT]),
+        "fasp_cuda_multicolor_host": (INT, [INT, T.PINT, T.PINT, T.PINT, T.PINT]),
         "fasp_cuda_smoother_dbsr_jacobi1": (INT, [P(dBSRmat), P(dvector), P(dvector), PREAL]),
         "fasp_cuda_dcsr_upload": (vp, [P(dCSRmat)]),
         "fasp_cuda_dcsr_free": (None, [vp]),

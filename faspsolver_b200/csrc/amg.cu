@@ -22,7 +22,8 @@ namespace fc {
 
 static bool smoother_supported(short s)
 {
-    return s == SMOOTHER_JACOBI || s == SMOOTHER_L1DIAG || s == SMOOTHER_POLY;
+    return s == SMOOTHER_JACOBI || s == SMOOTHER_L1DIAG || s == SMOOTHER_POLY ||
+           (s == SMOOTHER_GS && ctx().opt.gs_multicolor);
 }
 
 void amg_set_params(Amg& h, const AMG_param* p)
@@ -41,9 +42,21 @@ void amg_set_params(Amg& h, const AMG_param* p)
     h.maxit          = p->maxit;
 }
 
-static void level_smoother_data(Amg& h, Level& L)
+static void level_smoother_data(Amg& h, Level& L, const dCSRmat* hostA)
 {
     switch (h.smoother) {
+        case SMOOTHER_GS: {
+            std::vector<int> ic, icmap;
+            gs_multicolor_host(hostA->row, hostA->IA, hostA->JA, ic, icmap);
+            L.color_ptr  = ic;
+            L.ncolors    = (int)ic.size() - 1;
+            L.color_rows = dalloc<int>(icmap.size() ? icmap.size() : 1);
+            FC_CUDA(cudaMemcpyAsync(L.color_rows, icmap.data(), sizeof(int) * icmap.size(),
+                                    cudaMemcpyHostToDevice, ctx().stream));
+            FC_CUDA(cudaStreamSynchronize(ctx().stream));
+            h.bytes += sizeof(int) * icmap.size();
+            break;
+        }
         case SMOOTHER_JACOBI: csr_ensure_diag(L.A); break;
         case SMOOTHER_L1DIAG: csr_ensure_l1(L.A); break;
         case SMOOTHER_POLY: {
@@ -80,7 +93,8 @@ Amg* amg_upload(AMG_data* mgl, AMG_param* param)
              (int)param->cycle_type);
     if (nl > 1 && !smoother_supported(param->smoother))
         fail(ERROR_AMG_SMOOTH_TYPE,
-             "smoother %d has no data-parallel device form (supported: Jacobi 1, poly 9, L1 10)",
+             "smoother %d has no data-parallel device form (supported: Jacobi 1, poly 9, L1 10; "
+             "GS 2 as multicolour GS with option gs_multicolor=1, as FASP's OpenMP build does)",
              (int)param->smoother);
 
     Amg* h = new Amg();
@@ -99,7 +113,7 @@ Amg* amg_upload(AMG_data* mgl, AMG_param* param)
                 const dCSRmat& R = mgl[l].R;
                 csr_upload(L.P, P.row, P.col, P.nnz, P.IA, P.JA, P.val, ua);
                 csr_upload(L.R, R.row, R.col, R.nnz, R.IA, R.JA, R.val, ua);
-                level_smoother_data(*h, L);
+                level_smoother_data(*h, L, &A);
             }
             L.b  = dalloc<double>(L.n);
             L.xa = dalloc<double>(L.n);
@@ -159,6 +173,7 @@ struct CycleState {
     double*       x_out;    // where the final level-0 iterate must land
     Reduce        red;      // fused into the last kernel writing x_out when possible
     bool          red_done = false;
+    int           gs_order = 1;   // +1 pre-smoothing, -1 post-smoothing
     std::vector<double*> cur;     // current iterate buffer per level
     std::vector<bool>    xzero;   // iterate known to be identically zero
     CycleState(Amg& h_, const int* d) : h(h_), done(d), cur(h_.nl), xzero(h_.nl, false) {}
@@ -203,6 +218,14 @@ void smooth(CycleState& s, int l, int nsweeps, bool last)
                 }
                 if (final_sweep) s.red_done = true;
                 s.cur[l]   = out;
+                s.xzero[l] = false;
+                break;
+            }
+            case SMOOTHER_GS: {
+                // multicolour GS in place; pre-smoothing ascends the colours, post-smoothing
+                // descends (PreMGCycle.c:126-127, 253-254)
+                if (s.xzero[l]) vec_set(s.cur[l], 0.0, n, s.done);
+                gs_multicolor_sweeps(L.A, L.color_rows, L.color_ptr, b, s.cur[l], 1, s.gs_order, s.done);
                 s.xzero[l] = false;
                 break;
             }
@@ -301,6 +324,7 @@ void run_cycle(CycleState& s)
         while (l < nl - 1) {
             Level& L = h.lv[l];
             num_lvl[l]++;
+            s.gs_order = 1;
             smooth(s, l, h.presmooth, false);
             if (s.xzero[l]) {   // no pre-smoothing at all: x is still zero, residual = b
                 vec_set(s.cur[l], 0.0, L.n, s.done);
@@ -352,6 +376,7 @@ void run_cycle(CycleState& s)
             csr_launch(L.P, p);
             // the cycle ends when the backward sweep reaches level 0
             const bool last_level_visit = (l == 0);
+            s.gs_order = -1;
             smooth(s, l, h.postsmooth, last_level_visit);
             if (num_lvl[l] < ncycles[l]) break;
             num_lvl[l] = 0;

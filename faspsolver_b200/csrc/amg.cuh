@@ -47,6 +47,11 @@ struct Amg {
     long long kernels_per_cycle = 0;
 };
 
+// multicolour Gauss-Seidel (gs.cu)
+void gs_multicolor_host(int n, const int* IA, const int* JA, std::vector<int>& IC, std::vector<int>& ICMAP);
+void gs_multicolor_sweeps(const DevCSR& A, const int* color_rows, const std::vector<int>& color_ptr,
+                          const double* b, double* u, int L, int order, const int* done);
+
 // Build from a host hierarchy produced by FASP's setup (fasp.h:804-888).
 Amg* amg_upload(AMG_data* mgl, AMG_param* param);
 void amg_free(Amg* h);

@@ -162,6 +162,7 @@ static int* option_slot(const char* key)
     if (!strcmp(key, "pipe_tpb")) return &o.pipe_tpb;
     if (!strcmp(key, "rowwise_max")) return &o.rowwise_max;
     if (!strcmp(key, "vec_lpr")) return &o.vec_lpr;
+    if (!strcmp(key, "gs_multicolor")) return &o.gs_multicolor;
     return nullptr;
 }
 INT fasp_cuda_set_option(const char* key, double value)
@@ -1184,3 +1185,69 @@ INT fasp_cuda_solver_dbsr_krylov_amg(dBSRmat* A, dvector* b, dvector* x, ITS_par
 }
 
 } // extern "C"
+
+extern "C" {
+
+INT fasp_cuda_smoother_dcsr_gs_multicolor(dvector* u, dCSRmat* A, dvector* b, INT L, INT order)
+{
+    API_TRY
+    ensure_init();
+    check_csr(A);
+    std::vector<int> ic, icmap;
+    gs_multicolor_host(A->row, A->IA, A->JA, ic, icmap);
+    TmpCSR dA(A);
+    DVec   db(b->val, A->row), du(u->val, A->row);
+    int*   rows = dalloc<int>(icmap.size() ? icmap.size() : 1);
+    try {
+        FC_CUDA(cudaMemcpyAsync(rows, icmap.data(), sizeof(int) * icmap.size(), cudaMemcpyHostToDevice,
+                                ctx().stream));
+        gs_multicolor_sweeps(dA.m, rows, ic, db.p, du.p, L, order == -1 ? -1 : 1, nullptr);
+        du.to_host(u->val);
+    } catch (...) {
+        dfree(rows);
+        throw;
+    }
+    dfree(rows);
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+
+} // extern "C"
+
+#include "comm.cuh"
+extern "C" {
+INT fasp_cuda_comm_unique_id(void* id128)
+{
+    API_TRY
+    comm_unique_id(id128);
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+INT fasp_cuda_comm_init(const void* id128, int rank, int nranks)
+{
+    API_TRY
+    comm_init(id128, rank, nranks);
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+INT fasp_cuda_comm_finalize(void)
+{
+    API_TRY
+    comm_finalize();
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+int fasp_cuda_comm_rank(void) { return comm_rank(); }
+int fasp_cuda_comm_size(void) { return comm_size(); }
+} // extern "C"
+
+extern "C" INT fasp_cuda_multicolor_host(INT n, const INT* IA, const INT* JA, INT* IC, INT* ICMAP)
+{
+    API_TRY
+    std::vector<int> ic, icmap;
+    gs_multicolor_host(n, IA, JA, ic, icmap);
+    for (size_t i = 0; i < ic.size(); ++i) IC[i] = ic[i];
+    for (size_t i = 0; i < icmap.size(); ++i) ICMAP[i] = icmap[i];
+    return (INT)ic.size() - 1;
+    API_CATCH(code__)
+}

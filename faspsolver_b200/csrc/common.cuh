@@ -61,6 +61,7 @@ struct Options {
     int    pipe_tpb         = 128; // its threads per CTA = max rows per row block (64/128/256)
     int    rowwise_max      = 32;  // blocks averaging <= this many nonzeros per row: one thread per row
     int    vec_lpr          = 0;   // > 0: force this many lanes per row in the vector kernel
+    int    gs_multicolor    = 0;   // accept SMOOTHER_GS in the cycle as multicolour GS (OpenMP-FASP semantics)
     int    profile          = 0;   // record CUDA events around every matrix kernel (no graphs)
 };
 

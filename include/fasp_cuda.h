@@ -119,6 +119,9 @@ INT fasp_cuda_smoother_dcsr_poly(dCSRmat* Amat, dvector* brhs, dvector* usol, IN
 /* replaces fasp_smoother_dcsr_gs_multicolor BlaSparseCSR.c:2123 (colouring recomputed by the
  * library with the reference's greedy rule, BlaSparseCSR.c:1687)                         */
 INT fasp_cuda_smoother_dcsr_gs_multicolor(dvector* u, dCSRmat* A, dvector* b, INT L, INT order);
+/* the colouring itself (host, no GPU): IC[ncolors+1] offsets into ICMAP[row] as dCSRmat_Multicoloring
+ * (BlaSparseCSR.c:1687) would leave them in A->IC / A->ICMAP; returns the number of colours        */
+INT fasp_cuda_multicolor_host(INT n, const INT* IA, const INT* JA, INT* IC, INT* ICMAP);
 /* replaces fasp_smoother_dbsr_jacobi1  ItrSmootherBSR.c:263 (diaginv = inverted diagonal
  * blocks, nb*nb per block row, as produced by fasp_smoother_dbsr_jacobi_setup :163)      */
 INT fasp_cuda_smoother_dbsr_jacobi1(dBSRmat* A, dvector* b, dvector* u, REAL* diaginv);

@@ -1,0 +1,145 @@
+"""CPU tests (no GPU): the oracle restatement (oracle/fasp_oracle.c) is pinned against
+ (a) the committed golden vectors / answers produced by the unmodified reference, and
+ (b) the reference library itself (oracle/_ref/libfasp_seq.so) when it has been built here,
+including the reference's own golden log test/out/reg.gcc (via tests/golden/oracle_answers.json)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from faspsolver_b200 import fasp_types as T
+from faspsolver_b200 import problems as PB
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle.port import Oracle
+    return Oracle()
+
+
+def test_oracle_kernels_match_golden_vectors(orc, data, golden_vectors):
+    A, g, b = data["FE"], golden_vectors, data["FE_b"]
+    assert np.array_equal(orc.mxv(A, g["x"]), g["mxv"])
+    assert np.array_equal(orc.aAxpy(-1.0, A, g["x"], b), g["aAxpy_m1"])
+    assert np.array_equal(orc.aAxpy(0.3, A, g["x"], b), g["aAxpy_0p3"])
+    assert np.array_equal(orc.jacobi(A, b, g["x"], 2, 0.67), g["smooth_jacobi067"])
+    assert np.array_equal(orc.l1diag(A, b, g["x"], 2), g["smooth_l1diag"])
+    assert np.array_equal(orc.poly(A, b, g["x"], 3, 2), g["smooth_poly3"])
+
+
+def test_oracle_kernels_match_reference_live(orc, ref, data):
+    rng = np.random.default_rng(41)
+    for A in (data["FD"], data["FE"], PB.poisson7(12), PB.convdiff7(10), PB.poisson27(8)):
+        n = A.shape[0]
+        x, b = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+        assert np.array_equal(orc.mxv(A, x), ref.mxv(A, x))
+        assert np.array_equal(orc.aAxpy(0.7, A, x, b), ref.aAxpy(0.7, A, x, b))
+        u = T.Vec(x.copy())
+        ref.L.fasp_smoother_dcsr_L1diag(u.ptr(), 0, n - 1, 1, A.ptr(), T.Vec(b).ptr(), 2)
+        assert np.array_equal(orc.l1diag(A, b, x, 2), u.a)
+        u = T.Vec(x.copy())
+        ref.L.fasp_smoother_dcsr_jacobi(u.ptr(), n - 1, 0, -1, A.ptr(), T.Vec(b).ptr(), 3, 0.8)
+        assert np.array_equal(orc.jacobi(A, b, x, 3, 0.8), u.a)
+        u = T.Vec(x.copy())
+        ref.L.fasp_smoother_dcsr_poly(A.ptr(), T.Vec(b).ptr(), u.ptr(), n, 4, 1)
+        assert np.array_equal(orc.poly(A, b, x, 4, 1), u.a)
+
+
+def test_oracle_bsr_matches_reference(orc, ref, data):
+    from oracle.port import _pd, _pi
+    rng = np.random.default_rng(42)
+    for A in (data["SPE"], PB.blockoil7(4)[0]):
+        n = A.ROW * A.nb
+        x, y0 = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+        y, yr = np.empty(n), np.empty(n)
+        orc.L.oracle_dbsr_mxv(A.ROW, A.nb, _pi(A.ia), _pi(A.ja), _pd(A.val), _pd(x), _pd(y))
+        ref.L.fasp_blas_dbsr_mxv(A.ptr(), T.as_preal(x), T.as_preal(yr))
+        assert np.array_equal(y, yr)
+        for alpha in (1.0, -1.0, 0.4):
+            y, yr = y0.copy(), y0.copy()
+            orc.L.oracle_dbsr_aAxpy(alpha, A.ROW, A.nb, _pi(A.ia), _pi(A.ja), _pd(A.val), _pd(x), _pd(y))
+            ref.L.fasp_blas_dbsr_aAxpy(alpha, A.ptr(), T.as_preal(x), T.as_preal(yr))
+            assert np.array_equal(y, yr)
+        dinv = ref.L.fasp_dbsr_getdiaginv(A.ptr())
+        dnp = np.ctypeslib.as_array(dinv.val, shape=(A.ROW * A.nb * A.nb,)).copy()
+        u, ur = x.copy(), T.Vec(x.copy())
+        orc.L.oracle_dbsr_jacobi1(A.ROW, A.nb, _pi(A.ia), _pi(A.ja), _pd(A.val), _pd(y0), _pd(u), _pd(dnp))
+        ref.L.fasp_smoother_dbsr_jacobi1(A.ptr(), T.Vec(y0).ptr(), ur.ptr(), dinv.val)
+        assert np.array_equal(u, ur.a)
+
+
+ORACLE_SOLVES = [
+    ("FE_pcg_jacobi067", "pcg", {}), ("FE_pcg_l1", "pcg", {}), ("FE_pcg_poly3", "pcg", {}),
+    ("FE_pcg_l1_W", "pcg", {}), ("FE_gmres30_l1", "gmres", dict(variable=False)),
+    ("FE_vgmres30_poly3", "gmres", dict(variable=True)), ("FD_pcg_jacobi067_cdof20", "pcg", {}),
+    ("FD_pcg_l1_cdof20", "pcg", {}),
+]
+
+
+@pytest.mark.parametrize("name,method,kw", ORACLE_SOLVES)
+def test_oracle_solves_reproduce_reference_answers(orc, ref, data, golden_answers, name, method, kw):
+    """Iteration counts of the restated PCG / GMRES + V-cycle equal the committed answers of the
+    unmodified reference (hierarchy from the reference's own setup)."""
+    from oracle.port import OracleMG, hierarchy_from_mgl
+    rec = {r["name"]: r for r in golden_answers["recipes"]}[name]
+    prob = name.split("_")[0]
+    A, b = data[prob], data[prob + "_b"]
+    amg = ref.amg_param(print_level=0, **rec["amg"])
+    mgl = ref.amg_setup(A, amg)
+    try:
+        lv = hierarchy_from_mgl(mgl)
+    finally:
+        ref.amg_free(mgl, amg)
+    mg = OracleMG(orc, lv, smoother=amg.smoother, cycle_type=amg.cycle_type, presmooth=amg.presmooth_iter,
+                  postsmooth=amg.postsmooth_iter, ndeg=amg.polynomial_degree, relax=amg.relaxation, tol=1e-6)
+    if method == "pcg":
+        st, x, rel = mg.pcg(A, b, tol=1e-8)
+    else:
+        st, x, rel = mg.gmres(A, b, tol=1e-8, restart=rec["it"]["restart"], **kw)
+    mg.close()
+    assert st == rec["status"], (name, st, rec["status"])
+    assert np.linalg.norm(b - A.to_scipy() @ x) / np.linalg.norm(b) <= 1e-8 * 1.001
+
+
+def test_oracle_cycle_matches_reference_cycle(orc, ref, data):
+    from oracle.port import OracleMG, hierarchy_from_mgl
+    A, b = data["FE"], data["FE_b"]
+    for kw in (dict(smoother=T.SMOOTHER_L1DIAG), dict(smoother=T.SMOOTHER_JACOBI, relaxation=0.67, cycle_type=T.W_CYCLE),
+               dict(smoother=T.SMOOTHER_POLY, polynomial_degree=3, coarse_scaling=T.ON)):
+        amg = ref.amg_param(print_level=0, **kw)
+        mgl = ref.amg_setup(A, amg)
+        try:
+            n = A.shape[0]
+            np.ctypeslib.as_array(mgl[0].b.val, shape=(n,))[:] = b
+            np.ctypeslib.as_array(mgl[0].x.val, shape=(n,))[:] = 0.0
+            ref.L.fasp_solver_mgcycle(mgl, C.byref(amg))
+            x_ref = np.ctypeslib.as_array(mgl[0].x.val, shape=(n,)).copy()
+            lv = hierarchy_from_mgl(mgl)
+        finally:
+            ref.amg_free(mgl, amg)
+        mg = OracleMG(orc, lv, smoother=amg.smoother, cycle_type=amg.cycle_type, ndeg=amg.polynomial_degree,
+                      relax=amg.relaxation, coarse_scaling=amg.coarse_scaling, tol=amg.tol)
+        x = mg.cycle(b, np.zeros(n))
+        mg.close()
+        assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < 1e-9, kw
+
+
+def test_reference_reproduces_reg_gcc_golden_lines(ref, data, golden_answers):
+    """The compiled reference (our oracle's anchor) reproduces test/out/reg.gcc bit for bit on the
+    lines that pin this path: FE AMG-PCG 6 it / 2.728796e-11, FD 1 it / 4.938174e-15, and the
+    L1_DIAG AMG solver 19 it / 8.612004e-11."""
+    g = golden_answers["reg_gcc"]
+    for prob, key in (("FE", "FE_amg_pcg_default_tol1e-10"), ("FD", "FD_amg_pcg_default_tol1e-10")):
+        A, b = data[prob], data[prob + "_b"]
+        it = ref.its_param(maxit=500, tol=1e-10, print_level=0)
+        amg = ref.amg_param(print_level=0)
+        st, x = ref.krylov_amg(A, b, np.zeros_like(b), it, amg)
+        assert st == g[key]["iters"]
+        assert np.abs(x - data[prob + "_sol"]).max() < 1e-4
+    A, b = data["FE"], data["FE_b"]
+    amg = ref.amg_param(print_level=0, maxit=500, tol=1e-10, smoother=T.SMOOTHER_L1DIAG)
+    vb, vx = T.Vec(b), T.Vec(np.zeros_like(b))
+    st = ref.L.fasp_solver_amg(A.ptr(), vb.ptr(), vx.ptr(), C.byref(amg))
+    assert st == g["FE_amg_solver_L1DIAG_tol1e-10"]["iters"]
+    rel = np.linalg.norm(b - A.to_scipy() @ vx.a) / np.linalg.norm(b)
+    assert abs(rel - g["FE_amg_solver_L1DIAG_tol1e-10"]["relres"]) / rel < 1e-5
