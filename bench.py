@@ -244,8 +244,23 @@ def run_ours(args):
                                             "GBps": float(np.mean([b_ / m * 1e-6 for m, b_ in v]))}
                 for k, v in by_kind.items()}
     ach = float(sum(by for *_, by in lvl0) / l0_ms * 1e-6) if l0_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "csr_rowblock_kernel (level-0 A: SpMV / residual / L1 sweep)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    # DRAM traffic per launch of the same kernel from the committed ncu --set full capture
+    traffic, traffic_src = None, None
+    tf = ROOT / "profiles" / "r01_ncu_traffic.json"
+    if tf.exists() and args.n == 256:
+        tj = json.loads(tf.read_text())
+        ks = tj["kernels"]
+        per = {"resid": ks.get("resid"), "l1": ks.get("l1"), "mxv": ks.get("mxv") or ks.get("resid")}
+        num = sum(per[kind_names[k]]["traffic"] * len(v) for k, v in by_kind.items() if per.get(kind_names.get(k)))
+        den = sum(len(v) for k, v in by_kind.items() if per.get(kind_names.get(k)))
+        traffic = num / den if den else None
+        traffic_src = tj["source"]
+    alg_per_launch = float(np.mean([by for *_, by in lvl0])) if lvl0 else None
+    roofline = {"bound": "hbm", "kernel": "csr_pipe_kernel on the level-0 matrix (SpMV / residual / L1-Jacobi sweep), "
+                                          "CUDA events around every launch of one solve",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_per_launch,
+                "launch_ms": l0_ms / len(lvl0) if lvl0 else None,
                 "peak_source": peak_src, "share_of_matrix_kernel_time": l0_ms / tot_ms if tot_ms else None,
                 "per_mode": per_kind}
     # per-level table for profiles/
