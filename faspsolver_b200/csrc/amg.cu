@@ -17,6 +17,8 @@
 //   prolongate   x += P x_{l+1}           1 pass over P_l
 //   post-smooth  x = S(x)                 1 pass over A_l
 #include "amg.cuh"
+#include "comm.cuh"
+#include "dist.cuh"
 
 namespace fc {
 
@@ -42,7 +44,18 @@ void amg_set_params(Amg& h, const AMG_param* p)
     h.maxit          = p->maxit;
 }
 
-static void level_smoother_data(Amg& h, Level& L, const dCSRmat* hostA)
+void amg_level_vectors(Amg& h, Level& L)
+{
+    if (L.cap < L.n) L.cap = L.n;
+    const size_t c = (size_t)L.cap + 8;
+    L.b  = dalloc<double>(c);
+    L.xa = dalloc<double>(c);
+    L.xb = dalloc<double>(c);
+    L.w  = dalloc<double>(c);
+    h.bytes += 4 * sizeof(double) * c;
+}
+
+void amg_level_smoother_data(Amg& h, Level& L, const dCSRmat* hostA)
 {
     switch (h.smoother) {
         case SMOOTHER_GS: {
@@ -61,7 +74,16 @@ static void level_smoother_data(Amg& h, Level& L, const dCSRmat* hostA)
         case SMOOTHER_L1DIAG: csr_ensure_l1(L.A); break;
         case SMOOTHER_POLY: {
             // constants of fasp_smoother_dcsr_poly, ItrSmootherCSRpoly.c:94-107
-            double mu0        = 1.0 / csr_dinv_a_norminf(L.A);
+            double nrm = csr_dinv_a_norminf(L.A);
+            if (L.dist && comm_active()) {   // the norm is a maximum over ALL rows
+                double* d = dalloc<double>(1);
+                FC_CUDA(cudaMemcpyAsync(d, &nrm, sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+                comm_allreduce(d, 1, 2);
+                FC_CUDA(cudaMemcpyAsync(&nrm, d, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+                FC_CUDA(cudaStreamSynchronize(ctx().stream));
+                dfree(d);
+            }
+            double mu0        = 1.0 / nrm;
             const double mu1  = 4.0 * mu0;
             const double smu0 = sqrt(mu0), smu1 = sqrt(mu1);
             L.pk[1] = (mu0 + mu1) / 2.0;
@@ -71,8 +93,8 @@ static void level_smoother_data(Amg& h, Level& L, const dCSRmat* hostA)
             L.pk[5] = (mu1 - 2.0 * smu0 * smu1 + mu0) / (mu1 + 2.0 * smu0 * smu1 + mu0);
             for (int i = 0; i < 3; ++i)
                 if (!L.pv[i]) {
-                    L.pv[i] = dalloc<double>(L.n);
-                    h.bytes += sizeof(double) * (size_t)L.n;
+                    L.pv[i] = dalloc<double>((size_t)(L.cap > L.n ? L.cap : L.n) + 8);
+                    h.bytes += sizeof(double) * (size_t)(L.cap > L.n ? L.cap : L.n);
                 }
             break;
         }
@@ -113,13 +135,11 @@ Amg* amg_upload(AMG_data* mgl, AMG_param* param)
                 const dCSRmat& R = mgl[l].R;
                 csr_upload(L.P, P.row, P.col, P.nnz, P.IA, P.JA, P.val, ua);
                 csr_upload(L.R, R.row, R.col, R.nnz, R.IA, R.JA, R.val, ua);
-                level_smoother_data(*h, L, &A);
+                amg_level_smoother_data(*h, L, &A);
             }
-            L.b  = dalloc<double>(L.n);
-            L.xa = dalloc<double>(L.n);
-            L.xb = dalloc<double>(L.n);
-            L.w  = dalloc<double>(L.n);
-            h->bytes += L.A.bytes + L.P.bytes + L.R.bytes + 4 * sizeof(double) * (size_t)L.n;
+            L.nglobal = L.n;
+            amg_level_vectors(*h, L);
+            h->bytes += L.A.bytes + L.P.bytes + L.R.bytes;
         }
         h->scal = dalloc<double>(4);
         FC_CUDA(cudaMemsetAsync(h->scal, 0, 4 * sizeof(double), ctx().stream));
@@ -155,6 +175,9 @@ void amg_free(Amg* h)
         dfree(L.w);
         for (int i = 0; i < 3; ++i) dfree(L.pv[i]);
         dfree(L.color_rows);
+        halo_free(L.hA);
+        halo_free(L.hP);
+        halo_free(L.hR);
     }
     dense_free(h->coarse);
     dfree(h->scal);
@@ -342,7 +365,11 @@ void run_cycle(CycleState& s)
             r.x    = L.w;
             r.y    = h.lv[l + 1].b;
             r.done = s.done;
+            const bool gather_next = L.dist && !h.lv[l + 1].dist;   // agglomeration boundary
+            if (gather_next) r.y += L.gdispls[comm_rank()];
             csr_launch(L.R, r);
+            if (gather_next)
+                comm_allgatherv(r.y, L.gcounts[comm_rank()], h.lv[l + 1].b, L.gcounts, L.gdispls);
             ++l;
             s.cur[l]   = h.lv[l].xa;
             s.xzero[l] = true;   // fasp_dvec_set(..., 0.0) (:151) is folded into the next writer
@@ -362,12 +389,14 @@ void run_cycle(CycleState& s)
             p.done = s.done;
             if (h.coarse_scaling == ON) {   // (:210-216)
                 vec_dot(s.cur[l + 1], Lc.b, Lc.n, h.scal + 1, s.done);
+                if (Lc.dist) comm_allreduce(h.scal + 1, 1);
                 CsrArgs v;
                 v.mode         = CSR_MXV;
                 v.x            = s.cur[l + 1];
                 v.y            = Lc.w;
                 v.red.dot_with = s.cur[l + 1];
                 v.red.dot_out  = h.scal + 2;
+                v.red.global   = Lc.dist;
                 v.done         = s.done;
                 csr_launch(Lc.A, v);
                 scaling_alpha(h.scal, s.done);

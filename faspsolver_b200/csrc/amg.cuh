@@ -18,7 +18,12 @@ void dense_free(DenseInv& D);
 
 struct Level {
     DevCSR  A, P, R;          // P: level l <- l+1 ; R: level l+1 <- l   (R = P^T stored explicitly)
-    int     n  = 0;
+    int     n  = 0;          // local rows (= global rows on one GPU)
+    int     cap = 0;          // entries allocated per level vector: n + room for ghosts
+    bool    dist = false;     // multi-GPU: rows of this level are partitioned over the ranks
+    int     nglobal = 0, row0 = 0;
+    std::vector<size_t> gcounts, gdispls;   // next level replicated: every rank's slice of its vectors
+    HaloPlan *hA = nullptr, *hP = nullptr, *hR = nullptr;
     double* b  = nullptr;     // right-hand side on this level (level 0: caller's r)
     double* xa = nullptr;     // iterate ping-pong buffers
     double* xb = nullptr;
@@ -35,6 +40,8 @@ struct Level {
 struct Amg {
     std::vector<Level> lv;
     int    nl = 0;
+    bool   dist = false;            // multi-GPU hierarchy (dist.cu)
+    std::vector<int> off0;          // level-0 row partition (size nranks+1)
     // parameters (AMG_param / precond_data members used by the cycle, PreMGCycle.c:50-59)
     short  amg_type = CLASSIC_AMG, smoother = SMOOTHER_GS, cycle_type = V_CYCLE;
     short  presmooth = 1, postsmooth = 1, ndeg = 3, coarse_scaling = OFF, coarse_solver = 0;
@@ -56,6 +63,8 @@ void gs_multicolor_sweeps(const DevCSR& A, const int* color_rows, const std::vec
 Amg* amg_upload(AMG_data* mgl, AMG_param* param);
 void amg_free(Amg* h);
 void amg_set_params(Amg& h, const AMG_param* param);
+void amg_level_smoother_data(Amg& h, Level& L, const dCSRmat* hostA);
+void amg_level_vectors(Amg& h, Level& L);
 
 // One preconditioner application z = B r: x0 = 0, h.maxit cycles (PreCSR.c:416-435 +
 // PreMGCycle.c:48-274). r is used in place as the level-0 right-hand side; the result is

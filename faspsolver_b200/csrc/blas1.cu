@@ -129,6 +129,7 @@ void vec_scale_div(double* y, double s, const double* x, const double* d, size_t
     if (n == 0) return;
     const int g = vec_grid(n);
     FC_LAUNCH(k_scale_div, g, VT, 0, y, s, x, d, n, red, red_partials(g), red_ticket(), done);
+    reduce_finish(red);
 }
 void vec_dot(const double* x, const double* y, size_t n, double* out_dev, const int* done)
 {
@@ -142,6 +143,7 @@ void vec_reduce(const double* x, size_t n, const Reduce& red, const int* done)
     if (!red.dot_out && !red.nrm2_out) return;
     const int g = vec_grid(n ? n : 1);
     FC_LAUNCH(k_reduce, g, VT, 0, x, n, red, red_partials(g), red_ticket(), done);
+    reduce_finish(red);
 }
 void vec_mul(double* y, const double* d, const double* x, size_t n, const int* done)
 {

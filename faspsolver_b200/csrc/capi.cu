@@ -1251,3 +1251,61 @@ extern "C" INT fasp_cuda_multicolor_host(INT n, const INT* IA, const INT* JA, IN
     return (INT)ic.size() - 1;
     API_CATCH(code__)
 }
+
+// ------------------------------------------------------------------------------------
+// multi-GPU: row-partitioned hierarchy
+// ------------------------------------------------------------------------------------
+#include "dist.cuh"
+extern "C" {
+
+fasp_cuda_solver* fasp_cuda_dist_krylov_amg_create(AMG_data* mgl, AMG_param* amgparam, INT agg_rows)
+{
+    API_TRY
+    return solver_create_dist(mgl, amgparam, agg_rows);
+    API_CATCH(nullptr)
+}
+
+INT fasp_cuda_dist_row_range(const fasp_cuda_solver* s, INT* row_begin, INT* row_end)
+{
+    if (!s || !s->amg) return ERROR_INPUT_PAR;
+    const Amg& h = *s->amg;
+    if (h.dist && !h.off0.empty()) {
+        *row_begin = h.off0[comm_rank()];
+        *row_end   = h.off0[comm_rank() + 1];
+    } else {
+        *row_begin = 0;
+        *row_end   = h.lv[0].n;
+    }
+    return FASP_SUCCESS;
+}
+
+INT fasp_cuda_dist_extract_host(const dCSRmat* A, INT nranks, INT rank, INT* ia, INT* ja, INT* ghosts,
+                                INT ghost_cap, INT* nghost, INT* send_idx, INT send_cap, INT* send_counts)
+{
+    API_TRY
+    check_csr(A);
+    if (A->row != A->col) fail(ERROR_MAT_SIZE, "dist_extract_host: square operators only");
+    if (rank < 0 || rank >= nranks) fail(ERROR_INPUT_PAR, "rank out of range");
+    const std::vector<int> off = dist_partition(A->row, nranks);
+    LocalCSR               loc;
+    dist_extract(*A, off[rank], off[rank + 1], off, rank, false, loc);
+    for (size_t i = 0; i < loc.ia.size(); ++i) ia[i] = loc.ia[i];
+    for (size_t i = 0; i < loc.ja.size(); ++i) ja[i] = loc.ja[i];
+    *nghost = (INT)loc.ghosts.size();
+    if ((INT)loc.ghosts.size() > ghost_cap) fail(ERROR_INPUT_PAR, "ghost buffer too small");
+    for (size_t i = 0; i < loc.ghosts.size(); ++i) ghosts[i] = loc.ghosts[i];
+    std::vector<std::vector<int>> send;
+    dist_send_lists(*A, off, off, rank, send);
+    INT pos = 0;
+    for (int q = 0; q < nranks; ++q) {
+        send_counts[q] = (INT)send[q].size();
+        for (int c : send[q]) {
+            if (pos >= send_cap) fail(ERROR_INPUT_PAR, "send buffer too small");
+            send_idx[pos++] = c;
+        }
+    }
+    return (INT)loc.ja.size();
+    API_CATCH(code__)
+}
+
+} // extern "C"

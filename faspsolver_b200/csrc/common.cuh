@@ -126,6 +126,8 @@ template <class T> T* dalloc(size_t n) { return static_cast<T*>(dmalloc(n * size
 //                                 with <= blk_cap nonzeros and <= 256 rows, or one long row
 //   diag   f64[rows], dpos int32[rows]   diagonal entry and its offset in the row (Jacobi)
 //   l1     f64[rows]              sum_k |a_ik| in storage order (L1 smoother)
+struct HaloPlan;   // dist.cu: ghost exchange plan of a row-partitioned operator
+
 struct DevCSR {
     int       rows = 0, cols = 0;
     long long nnz  = 0;
@@ -144,6 +146,8 @@ struct DevCSR {
     double*   dinv = nullptr;     // 1/diag (first stored diagonal entry), poly smoother
     size_t    bytes = 0;
     bool      dup_diag = false;   // some row stores more than one (i,i) entry
+    int       nghost = 0;         // multi-GPU: ghost entries behind the owned part of a gathered vector
+    HaloPlan* halo = nullptr;     // multi-GPU: ghosts of the gathered vector are exchanged before the kernel
 };
 
 // Upload a host CSR (FASP layout). `pattern_only` drops the values (UA-AMG P/R: all ones).
@@ -173,7 +177,12 @@ struct Reduce {
     const double* dot_with = nullptr;  // sum out_i * dot_with[i]
     double*       dot_out  = nullptr;  // device scalar
     double*       nrm2_out = nullptr;  // device scalar: sum out_i^2  (not square-rooted)
+    bool          global   = false;    // multi-GPU: the sums are all-reduced over the ranks
 };
+// all-reduce the outputs of a fused reduction when it is global and a communicator is active
+void reduce_finish(const Reduce& red);
+// ghost exchange (dist.cu); x must have room for the plan's ghosts behind its owned entries
+void halo_exchange(const HaloPlan& h, double* x);
 
 // ------------------------------------------------------------------------------------
 // CSR row kernels (spmv.cu)

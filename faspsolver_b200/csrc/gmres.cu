@@ -14,6 +14,7 @@
 // per entry.
 #include "krylov.cuh"
 #include "reduce.cuh"
+#include "comm.cuh"
 
 namespace fc {
 
@@ -288,7 +289,7 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
     const long long launches0   = c.launches;
     const int       restart_max = variable ? restart : (restart < MaxIt ? restart : (MaxIt > 0 ? MaxIt : 1));
     const int       R           = restart_max;
-    const size_t    ldp         = (n + 1) & ~(size_t)1;
+    const size_t    ldp         = (A.vec_capacity() + 1) & ~(size_t)1;   // room for ghosts
     const int       hcap        = MaxIt + 2;
 
     double*   work = nullptr;
@@ -345,10 +346,12 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
         FC_CUDA(cudaEventRecord(t0, c.stream));
         {
             Reduce red;
+            red.global = true;
             red.nrm2_out = &st->rr;
             A.apply(CSR_RESID, 1.0, x, b, pvec(0), red, nullptr);
             if (StopType == STOP_MOD_REL_RES) {
                 Reduce rx;
+            rx.global = true;
                 rx.nrm2_out = &st->xx;
                 vec_reduce(x, n, rx, nullptr);
             }
@@ -363,8 +366,11 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
             pc.apply(pvec(i - 1), r, Reduce(), gate);
             A.apply(CSR_MXV, 1.0, r, nullptr, pvec(i), Reduce(), gate);
             for (int j = 0; j <= i; ++j)
+            {
                 FC_LAUNCH(k_gm_mgs, g, 256, 0, st, hh, j, i, j > 0 ? pvec(j - 1) : nullptr,
                           j < i ? pvec(j) : nullptr, pvec(i), n, red_partials(g), red_ticket());
+                comm_allreduce(j < i ? hh + (size_t)j * R + (i - 1) : &st->t2, 1);
+            }
             FC_LAUNCH(k_gm_givens, 1, 1, 0, st, hh, cc, ss, rs, norms, habs, i);
             FC_LAUNCH(k_gm_scale, g, 256, 0, st, &st->skip_scale, pvec(i), n);
         };
@@ -380,10 +386,12 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
             FC_LAUNCH(k_gm_add, g, 256, 0, st, r, x, n);
             FC_LAUNCH(k_gm_after_update, 1, 1, 0, st);
             Reduce red;
+            red.global = true;
             red.nrm2_out = &st->rr;
             A.apply(CSR_RESID, 1.0, x, b, r, red, &st->skip_true, true);
             if (StopType == STOP_MOD_REL_RES) {
                 Reduce rx;
+            rx.global = true;
                 rx.nrm2_out = &st->xx;
                 vec_reduce(x, n, rx, &st->skip_true);
             }

@@ -13,6 +13,7 @@
 // tests convergence synchronously.
 #include "krylov.cuh"
 #include "reduce.cuh"
+#include "comm.cuh"
 
 namespace fc {
 
@@ -315,6 +316,7 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
     ensure_init();
     Ctx&         c = ctx();
     const size_t n = (size_t)A.n;
+    const size_t ncap = A.vec_capacity();   // n + room for ghost entries (multi-GPU)
     if (StopType != STOP_REL_RES && StopType != STOP_MOD_REL_RES)
         fail(ERROR_INPUT_PAR,
              "device PCG supports stop_type STOP_REL_RES (1) and STOP_MOD_REL_RES (3), got %d",
@@ -327,9 +329,10 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
     const int       hcap      = MaxIt + 2;
     const int       look      = c.opt.lookahead < 1 ? 1 : c.opt.lookahead;
     // (re)build the workspace when the shape changes; graphs are tied to the buffers
-    if (W.n != n || W.hcap != hcap || W.look != look) {
+    if (W.n != n || W.ncap != ncap || W.hcap != hcap || W.look != look) {
         W.release();
-        W.work = dalloc<double>(4 * n + 3 * (size_t)hcap);
+        W.work = dalloc<double>(4 * ncap + 3 * (size_t)hcap);
+        W.ncap = ncap;
         W.st   = static_cast<void*>(dalloc<PcgState>(1));
         FC_CUDA(cudaMallocHost(&W.pin, sizeof(int) * 4 * (look + 1)));
         W.ev.resize(look + 1);
@@ -347,8 +350,8 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
         W.kepoch = c.opt_epoch;
     }
     double *  work = W.work;
-    double *  p = work, *z = p + n, *r = z + n, *t = r + n;
-    double *  hr = t + n, *ha = hr + hcap, *hf = ha + hcap;
+    double *  p = work, *z = p + ncap, *r = z + ncap, *t = r + ncap;
+    double *  hr = t + ncap, *ha = hr + hcap, *hf = ha + hcap;
     PcgState* st  = static_cast<PcgState*>(W.st);
     int*      pin = W.pin;
     std::vector<cudaEvent_t>& ev = W.ev;
@@ -376,14 +379,17 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
         // r = b - A u ; z = B r ; p = z ; temp1 = (z,r)
         auto initial = [&]() {
             Reduce red;
+            red.global = true;
             red.nrm2_out = &st->rr;
             A.apply(CSR_RESID, 1.0, u, b, r, red, nullptr);
             if (StopType == STOP_MOD_REL_RES) {
                 Reduce ru;
+            ru.global = true;
                 ru.nrm2_out = &st->uu;
                 vec_reduce(u, n, ru, nullptr);
             }
             Reduce rz;
+            rz.global = true;
             rz.dot_with = r;
             rz.dot_out  = &st->zr;
             pc.apply(r, z, rz, nullptr);
@@ -394,15 +400,22 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
 
         auto iteration = [&]() {
             Reduce rt;   // t = A p, tp = (t,p)
+            rt.global = true;
             rt.dot_with = p;
             rt.dot_out  = &st->tp;
             A.apply(CSR_MXV, 1.0, p, nullptr, t, rt, done);
             FC_LAUNCH(k_pcg_update, g, 256, 0, st, p, t, u, r, n, red_partials(g), red_ticket());
+            comm_allreduce(&st->rr, 1);
             FC_LAUNCH(k_pcg_check, 1, 1, 0, st, hr, ha, hf);
             // slow convergence: stagnation test and possible restart
             FC_LAUNCH(k_pcg_stag_norms, g, 256, 0, st, u, p, n, red_partials(g), red_ticket());
+            if (comm_active()) {   // branch-gated kernel: the flags are identical on every rank
+                comm_allreduce(&st->uinf, 1, 2);
+                comm_allreduce(&st->uu, 2, 0);
+            }
             FC_LAUNCH(k_pcg_stag_check, 1, 1, 0, st);
             Reduce rr;
+            rr.global = true;
             rr.nrm2_out = &st->rr;
             A.apply(CSR_RESID, 1.0, u, b, r, rr, &st->skip_stag2, true);
             FC_LAUNCH(k_pcg_stag_check2, 1, 1, 0, st);
@@ -411,6 +424,7 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
             FC_LAUNCH(k_pcg_cand_check, 1, 1, 0, st);
             // z = B r, zr = (z,r)
             Reduce rz;
+            rz.global = true;
             rz.dot_with = r;
             rz.dot_out  = &st->zr;
             pc.apply(r, z, rz, done);

@@ -10,6 +10,7 @@ struct LinOp {
     int n = 0;
     virtual ~LinOp() {}
     virtual const void* key() const { return this; }   // identity of the resident operator
+    virtual size_t      vec_capacity() const { return (size_t)n; }   // entries a gathered vector must hold
     // mode: CSR_MXV / CSR_AXPY / CSR_RESID semantics
     virtual void apply(int mode, double alpha, const double* x, const double* b, double* y,
                        const Reduce& red, const int* done, bool conditional = false) = 0;
@@ -18,6 +19,7 @@ struct CsrOp : LinOp {
     const DevCSR* A;
     explicit CsrOp(const DevCSR* a) : A(a) { n = a->rows; }
     const void* key() const override { return A; }
+    size_t      vec_capacity() const override { return (size_t)A->rows + (size_t)A->nghost; }
     void apply(int mode, double alpha, const double* x, const double* b, double* y,
                const Reduce& red, const int* done, bool conditional = false) override
     {
@@ -114,7 +116,7 @@ struct PcgCache {
     double* work = nullptr;
     void*   st   = nullptr;
     int*    pin  = nullptr;
-    size_t  n    = 0;
+    size_t  n    = 0, ncap = 0;
     int     hcap = 0, look = 0;
     std::vector<cudaEvent_t> ev;
     cudaEvent_t   t0 = nullptr, t1 = nullptr;

@@ -50,6 +50,26 @@ fasp_cuda_solver_s* solver_create_csr(AMG_data* mgl, AMG_param* amgparam)
     return s;
 }
 
+fasp_cuda_solver_s* solver_create_dist(AMG_data* mgl, AMG_param* amgparam, int agg_rows)
+{
+    ensure_init();
+    fasp_cuda_solver_s* s = new fasp_cuda_solver_s();
+    try {
+        AMG_param p = *amgparam;
+        p.tol       = 1e-6;
+        s->amg      = dist_amg_upload(mgl, &p, agg_rows);
+        s->n        = (size_t)s->amg->lv[0].n;                 // local rows
+        const size_t cap = (size_t)s->amg->lv[0].cap + 8;      // + ghosts of the level-0 operator
+        s->d_b      = dalloc<double>(cap);
+        s->d_x      = dalloc<double>(cap);
+        FC_CUDA(cudaMallocHost(&s->pin, sizeof(double) * 2 * s->n));
+    } catch (...) {
+        solver_destroy(s);
+        throw;
+    }
+    return s;
+}
+
 fasp_cuda_solver_s* solver_create_bsr(AMG_data_bsr* mgl, AMG_param* amgparam)
 {
     ensure_init();

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "amg.cuh"
 #include "krylov.cuh"
+#include "dist.cuh"
 
 struct fasp_cuda_solver_s {
     fc::Amg*       amg  = nullptr;     // CSR hierarchy (level-0 A doubles as the Krylov operator)
@@ -50,6 +51,7 @@ void      require_host_fasp();
 
 fasp_cuda_solver_s* solver_create_csr(AMG_data* mgl, AMG_param* amgparam);
 fasp_cuda_solver_s* solver_create_bsr(AMG_data_bsr* mgl, AMG_param* amgparam);
+fasp_cuda_solver_s* solver_create_dist(AMG_data* mgl, AMG_param* amgparam, int agg_rows);
 void                solver_destroy(fasp_cuda_solver_s* s);
 int    solver_solve_dev(fasp_cuda_solver_s* s, const double* b_dev, double* x_dev, ITS_param* it);
 int    solver_solve_host(fasp_cuda_solver_s* s, const double* b, double* x, ITS_param* it);

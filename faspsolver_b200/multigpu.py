@@ -1,0 +1,193 @@
+"""Multi-GPU host plumbing: one process per GPU (torchrun), torch.distributed only bootstraps the
+NCCL communicator of libfasp_cuda (unique id broadcast) and reduces timings; the data path is
+entirely inside the library (halo send/recv, all-reduce, all-gather over NVLink / NVSwitch).
+
+Also holds the CPU-side (numpy) restatement of the slab extraction used by the gloo tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import api
+from . import fasp_types as T
+
+
+def dist_env():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def init_comm(backend=None):
+    """Initialise torch.distributed (env:// rendezvous) and the library's NCCL communicator."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    L = api.lib()
+    api.check(L.fasp_cuda_init(local))
+    if world == 1:
+        return rank, world, local
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group(backend=backend or "gloo", rank=rank, world_size=world)
+    ident = (C.c_ubyte * 128)()
+    if rank == 0:
+        api.check(L.fasp_cuda_comm_unique_id(ident))
+    box = [bytes(ident)]
+    dist.broadcast_object_list(box, src=0)
+    buf = (C.c_ubyte * 128).from_buffer_copy(box[0])
+    api.check(L.fasp_cuda_comm_init(buf, rank, world))
+    return rank, world, local
+
+
+def allreduce_max(x: float) -> float:
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        return x
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def barrier():
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.barrier()
+
+
+class DistSolver(api.KrylovAmgSolver):
+    """Row-partitioned solver: b / x are this rank's local slices (rows [row0, row1))."""
+
+    def __init__(self, mgl, amgparam, agg_rows=200_000):
+        L = api.lib()
+        self.h = L.fasp_cuda_dist_krylov_amg_create(mgl, C.byref(amgparam), int(agg_rows))
+        if not self.h:
+            raise api.FaspCudaError(-1, api.last_error())
+        b, e = C.c_int(0), C.c_int(0)
+        api.check(L.fasp_cuda_dist_row_range(self.h, C.byref(b), C.byref(e)))
+        self.row0, self.row1 = b.value, e.value
+
+
+# ---------------------------------------------------------------------------------------
+# bench.py --gpus N
+# ---------------------------------------------------------------------------------------
+def bench_main(args):
+    import bench as B   # repo-root bench.py (helpers: problem, recipe, clocks, peaks)
+    rank, world, local = init_comm()
+    L = api.lib()
+    for kv in getattr(args, "opt", []):
+        k, v = kv.split("=")
+        api.check(L.fasp_cuda_set_option(k.encode(), float(v)))
+    log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
+
+    hf = B.host_fasp()
+    A, b = B.build_problem(args.n) if rank == 0 else _quiet(B.build_problem, args.n)
+    n = A.shape[0]
+    amg, it = B.amg_recipe(hf)
+    t = time.time()
+    mgl = hf.amg_setup(A, amg)          # every rank builds the same hierarchy (deterministic host setup)
+    t_setup = time.time() - t
+    info = api.hierarchy_info(mgl)
+    log("[bench] host AMG setup on every rank: %.1fs, %d levels" % (t_setup, len(info)))
+    t = time.time()
+    solver = DistSolver(mgl, amg, agg_rows=args.agg_rows)
+    t_upload = time.time() - t
+    hf.amg_free(mgl, amg)
+    r0, r1 = solver.row0, solver.row1
+    nloc = r1 - r0
+    b_loc = np.ascontiguousarray(b[r0:r1])
+    zero = np.zeros(nloc)
+    log("[bench] rank 0 owns rows [%d, %d) of %d; upload %.2fs" % (r0, r1, n, t_upload))
+
+    def host_solve():
+        st, x = solver.solve(b_loc, zero, it)
+        if st < 0:
+            raise RuntimeError("solve failed on rank %d: %d %s" % (rank, st, api.last_error()))
+        return st, x
+
+    for _ in range(args.warmup):
+        iters, _x = host_solve()
+    barrier()
+    sampler = B.ClockSampler(local)
+    sampler.start()
+    L.fasp_cuda_launch_count_reset()
+    dev_ms, e2e_ms = [], []
+    for _ in range(args.steps):
+        barrier()
+        iters, x_loc = host_solve()
+        dev_ms.append(allreduce_max(solver.stat(2)))     # device time of the Krylov loop, max over ranks
+        e2e_ms.append(allreduce_max(solver.stat(4)))     # incl. staging + H2D/D2H of the local slices
+    launches = int(L.fasp_cuda_launch_count())
+    clocks = sampler.stop()
+    barrier()
+    # true residual of the assembled solution (rank 0)
+    import torch
+    import torch.distributed as dist
+    parts = [None] * world
+    dist.all_gather_object(parts, (r0, x_loc))
+    out = None
+    if rank == 0:
+        x = np.empty(n)
+        for p0, xp in parts:
+            x[p0:p0 + xp.size] = xp
+        true_rel = float(np.linalg.norm(b - A.to_scipy() @ x) / np.linalg.norm(b))
+        if not true_rel <= 1e-8 * 1.001:
+            raise RuntimeError("assembled solution misses the tolerance: %g" % true_rel)
+        ms = float(np.mean(dev_ms))
+        out = {
+            "metric": B.METRIC, "value": ms, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: 3D 7-point Poisson %d^3 (%d rows, %d nnz), rhs=1, AMG-PCG tol 1e-8, "
+                                   "classical RS (FASP host setup), V(1,1) L1-Jacobi; rows partitioned over %d GPUs, "
+                                   "levels below %d rows replicated" % (args.n, n, A.nnz, world, args.agg_rows),
+                       "levels": len(info), "iterations": int(iters), "true_relres": true_rel,
+                       "l2_policy": "inputs larger than L2", "setup_s_host": t_setup, "upload_s": t_upload,
+                       "parallelism": "row slabs x%d, NCCL halo send/recv + allreduce" % world},
+            "e2e": {"value": float(np.mean(e2e_ms)), "unit": B.UNIT, "h2d_bytes_per_step": int(16 * nloc),
+                    "d2h_bytes_per_step": int(8 * nloc)},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": None, "cpu_baseline": None,
+        }
+    solver.close()
+    L.fasp_cuda_comm_finalize()
+    return out
+
+
+def _quiet(fn, *a):
+    import contextlib
+    import io
+    with contextlib.redirect_stderr(io.StringIO()):
+        return fn(*a)
+
+
+# ---------------------------------------------------------------------------------------
+# CPU helpers for the gloo tests
+# ---------------------------------------------------------------------------------------
+def extract_host(A: T.CSR, nranks: int, rank: int):
+    """The library's host-side slab extraction (no GPU): local ia/ja, ghost columns, send lists."""
+    L = api.lib()
+    n = A.shape[0]
+    off = [(n * r) // nranks for r in range(nranks + 1)]
+    r0, r1 = off[rank], off[rank + 1]
+    nnz_loc = int(A.ia[r1] - A.ia[r0])
+    ia = np.zeros(r1 - r0 + 1, dtype=np.int32)
+    ja = np.zeros(max(nnz_loc, 1), dtype=np.int32)
+    ghosts = np.zeros(max(nnz_loc, 1), dtype=np.int32)
+    send_idx = np.zeros(max(r1 - r0, 1) * max(nranks - 1, 1), dtype=np.int32)
+    send_counts = np.zeros(nranks, dtype=np.int32)
+    ng = C.c_int(0)
+    pi = lambda a: a.ctypes.data_as(T.PINT)
+    st = L.fasp_cuda_dist_extract_host(A.ptr(), nranks, rank, pi(ia), pi(ja), pi(ghosts), ghosts.size, C.byref(ng),
+                                       pi(send_idx), send_idx.size, pi(send_counts))
+    api.check(st)
+    val = A.val[A.ia[r0]:A.ia[r1]].copy()
+    return dict(off=off, ia=ia, ja=ja[:nnz_loc], val=val, ghosts=ghosts[:ng.value],
+                send_idx=send_idx[:int(send_counts.sum())], send_counts=send_counts)

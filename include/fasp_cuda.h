@@ -295,6 +295,19 @@ INT fasp_cuda_comm_finalize(void);
 int fasp_cuda_comm_rank(void);
 int fasp_cuda_comm_size(void);
 
+/* Row-partitioned solver: every rank passes the SAME host hierarchy (FASP's deterministic setup run
+ * redundantly); levels with >= agg_rows global rows are split into contiguous row slabs (rank r owns
+ * rows [begin, end) of level 0, see _row_range), smaller levels are replicated. The object is used
+ * with fasp_cuda_krylov_amg_solve / _solve_dev / _destroy; b and x are the rank's LOCAL slices.    */
+fasp_cuda_solver* fasp_cuda_dist_krylov_amg_create(AMG_data* mgl, AMG_param* amgparam, INT agg_rows);
+INT fasp_cuda_dist_row_range(const fasp_cuda_solver* s, INT* row_begin, INT* row_end);
+/* Host-only (no GPU, no communicator): the local slab of a square operator for `rank` of `nranks`:
+ * local ia/ja (columns renumbered [owned | ghosts]), the ghosts' global columns, and per peer the
+ * owned local indices that peer needs (send_idx concatenated by peer, send_counts[nranks]).
+ * Returns the local nnz or ERROR_*. Used by the CPU (gloo) tests of the partition logic.       */
+INT fasp_cuda_dist_extract_host(const dCSRmat* A, INT nranks, INT rank, INT* ia, INT* ja, INT* ghosts,
+                                INT ghost_cap, INT* nghost, INT* send_idx, INT send_cap, INT* send_counts);
+
 #ifdef __cplusplus
 }
 #endif

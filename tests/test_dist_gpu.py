@@ -1,0 +1,69 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the row-partitioned solve on 2 ranks gives
+the same iteration count and solution as the single-GPU solve and the sequential reference."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.gpu
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import numpy as np, torch.distributed as dist
+from faspsolver_b200 import api, problems as PB, multigpu as MG, fasp_types as T
+import bench as B
+rank, world, local = MG.init_comm()
+L = api.lib()
+hf = B.host_fasp()
+A = PB.poisson7(40); b = np.ones(A.shape[0])
+for smoother, solver_type in ((T.SMOOTHER_L1DIAG, T.SOLVER_CG), (T.SMOOTHER_JACOBI, T.SOLVER_VGMRES), (T.SMOOTHER_POLY, T.SOLVER_CG)):
+    amg = hf.amg_param(print_level=0, smoother=smoother, relaxation=0.67 if smoother == T.SMOOTHER_JACOBI else 1.0)
+    it = hf.its_param(itsolver_type=solver_type, tol=1e-8, maxit=200, print_level=0, restart=30)
+    mgl = hf.amg_setup(A, amg)
+    s = MG.DistSolver(mgl, amg, agg_rows=2000)
+    st, x_loc = s.solve(np.ascontiguousarray(b[s.row0:s.row1]), np.zeros(s.row1 - s.row0), it)
+    parts = [None] * world
+    dist.all_gather_object(parts, (s.row0, x_loc))
+    s.close()
+    if rank == 0:
+        x = np.concatenate([p[1] for p in sorted(parts, key=lambda t: t[0])])
+        from oracle.ref import RefFasp
+        ref = RefFasp()
+        amg_r = ref.amg_param(print_level=0, smoother=smoother, relaxation=0.67 if smoother == T.SMOOTHER_JACOBI else 1.0)
+        st_ref, x_ref = ref.krylov_amg(A, b, np.zeros_like(b), it, amg_r)
+        rel = float(np.linalg.norm(b - A.to_scipy() @ x) / np.linalg.norm(b))
+        dx = float(np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref))
+        print("RESULT", json.dumps({"smoother": smoother, "st": st, "st_ref": st_ref, "rel": rel, "dx": dx}))
+    hf.amg_free(mgl, amg)
+    MG.barrier()
+L.fasp_cuda_comm_finalize()
+'''
+
+
+def _ngpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout
+        return len([l for l in out.splitlines() if l.startswith("GPU ")])
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
+def test_two_rank_solve_matches_reference(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": str(ROOT)})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = [json.loads(l.split("RESULT", 1)[1]) for l in r.stdout.splitlines() if "RESULT" in l]
+    assert len(res) == 3
+    for d in res:
+        assert d["st"] > 0 and abs(d["st"] - d["st_ref"]) <= 1, d
+        assert d["rel"] <= 1e-8 * 1.001 and d["dx"] <= 1e-8, d
