@@ -104,6 +104,7 @@ void comm_allreduce(double* buf, size_t count, int op)
 {
     if (!comm_active()) return;
     Ctx& c = ctx();
+    ProfScope prof(401, (int)count, 0, 8.0 * count);
     nccl_check(N().AllReduce(buf, buf, count, ncclDouble, op == 2 ? ncclMax : ncclSum, N().comm, c.stream),
                "ncclAllReduce");
 }
@@ -120,6 +121,7 @@ void comm_allgatherv(const double* send, size_t sendcount, double* recv, const s
         return;
     }
     // variable counts: one broadcast per root inside a group (fused by NCCL into one launch)
+    ProfScope prof(402, (int)sendcount, 0, 8.0 * sendcount);
     nccl_check(n.GroupStart(), "ncclGroupStart");
     for (int r = 0; r < n.size; ++r)
         nccl_check(n.Broadcast(r == n.rank ? (const void*)send : (const void*)(recv + displs[r]),

@@ -105,7 +105,8 @@ void ensure_init();
 
 // profiling scope: records events around the enclosed launches when opt.profile is on
 struct ProfScope {
-    bool on;
+    bool   on;
+    size_t idx = 0;   // record index (scopes nest: a halo exchange inside a matrix kernel)
     ProfScope(int kind, int rows, long long nnz, double bytes);
     ~ProfScope();
 };

@@ -87,11 +87,12 @@ ProfScope::ProfScope(int kind, int rows, long long nnz, double bytes)
     cudaEventCreate(&r.e1);
     r.kind = kind, r.rows = rows, r.nnz = nnz, r.bytes = bytes;
     cudaEventRecord(r.e0, c.stream);
+    idx = c.prof.size();
     c.prof.push_back(r);
 }
 ProfScope::~ProfScope()
 {
-    if (on) cudaEventRecord(ctx().prof.back().e1, ctx().stream);
+    if (on) cudaEventRecord(ctx().prof[idx].e1, ctx().stream);
 }
 
 // The partial buffer only ever grows, and superseded buffers stay alive: captured CUDA

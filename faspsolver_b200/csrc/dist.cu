@@ -36,6 +36,7 @@ __global__ void k_halo_pack(int n, const int* __restrict__ idx, const double* __
 void halo_exchange(const HaloPlan& h, double* x)
 {
     if (!comm_active() || (h.nsend == 0 && h.nghost == 0)) return;
+    ProfScope prof(400, h.nloc, h.nsend + h.nghost, 8.0 * (h.nsend + h.nghost));
     if (h.nsend > 0) {
         int g = (h.nsend + 255) / 256;
         if (g > 1184) g = 1184;

@@ -658,8 +658,8 @@ void csr_launch(const DevCSR& A, const CsrArgs& a)
     double     pbytes  = csr_spmv_bytes(A, reads_y);
     if (a.mode == CSR_JACOBI || a.mode == CSR_L1) pbytes += 16.0 * A.rows;   // + u read, d read
     if (a.mode >= CSR_POLY1) pbytes += 16.0 * A.rows;
-    ProfScope  prof(a.conditional ? a.mode + 50 : a.mode, A.rows, A.nnz, pbytes);
     if (A.halo) halo_exchange(*A.halo, const_cast<double*>(a.x));
+    ProfScope  prof(a.conditional ? a.mode + 50 : a.mode, A.rows, A.nnz, pbytes);
     CsrView v{A.ia, A.ja, A.val, A.rowblk, A.blkdesc, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap, ctx().opt.rowwise_max};
     switch (a.mode) {
         case CSR_MXV: launch_mode<CSR_MXV>(A, v, a); break;

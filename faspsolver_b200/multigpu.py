@@ -42,7 +42,16 @@ def init_comm(backend=None):
     box = [bytes(ident)]
     dist.broadcast_object_list(box, src=0)
     buf = (C.c_ubyte * 128).from_buffer_copy(box[0])
-    api.check(L.fasp_cuda_comm_init(buf, rank, world))
+    # NCCL may print a version banner on stdout; bench.py's stdout must stay one JSON line
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        api.check(L.fasp_cuda_comm_init(buf, rank, world))
+        api.check(L.fasp_cuda_sync())
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
     return rank, world, local
 
 
