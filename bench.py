@@ -378,7 +378,7 @@ def main():
     ap.add_argument("--cpu-sample-iters", type=int, default=3)
     ap.add_argument("--ref-sample-iters", type=int, default=2)
     ap.add_argument("--opt", action="append", default=[], help="libfasp_cuda option key=value")
-    ap.add_argument("--agg-rows", type=int, default=200000,
+    ap.add_argument("--agg-rows", type=int, default=8000,
                     help="multi-GPU: levels with fewer global rows are replicated instead of partitioned")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -19,6 +19,7 @@
 #include "amg.cuh"
 #include "comm.cuh"
 #include "dist.cuh"
+#include "p2p.cuh"
 
 namespace fc {
 
@@ -166,6 +167,11 @@ void amg_free(Amg* h)
 {
     if (!h) return;
     for (Level& L : h->lv) {
+        if (L.p2p_registered) {
+            p2p_unregister(L.b), p2p_unregister(L.xa), p2p_unregister(L.xb), p2p_unregister(L.w);
+            for (int i = 0; i < 3; ++i)
+                if (L.pv[i]) p2p_unregister(L.pv[i]);
+        }
         csr_free(L.A);
         csr_free(L.P);
         csr_free(L.R);

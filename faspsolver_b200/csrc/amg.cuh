@@ -24,6 +24,7 @@ struct Level {
     int     nglobal = 0, row0 = 0;
     std::vector<size_t> gcounts, gdispls;   // next level replicated: every rank's slice of its vectors
     HaloPlan *hA = nullptr, *hP = nullptr, *hR = nullptr;
+    bool    p2p_registered = false;
     double* b  = nullptr;     // right-hand side on this level (level 0: caller's r)
     double* xa = nullptr;     // iterate ping-pong buffers
     double* xb = nullptr;

@@ -2,6 +2,7 @@
 // so the cost of the small messages on this path (halo faces, 1-3 scalars) is latency, not
 // link count; all operations are enqueued on the library stream and are graph-capturable.
 #include "comm.cuh"
+#include "p2p.cuh"
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -86,6 +87,7 @@ void comm_init(const void* id128, int rank, int nranks)
     nccl_check(n.CommInitRank(&n.comm, nranks, id, rank), "ncclCommInitRank");
     n.rank = rank;
     n.size = nranks;
+    p2p_init();   // peer-memory data path when CUDA IPC is available (else NCCL everywhere)
 }
 
 void comm_finalize()
@@ -93,6 +95,7 @@ void comm_finalize()
     Nccl& n = N();
     if (n.comm) {
         cudaStreamSynchronize(ctx().stream);
+        p2p_finalize();
         n.CommDestroy(n.comm);
     }
     n.comm = nullptr;
@@ -103,6 +106,10 @@ void comm_finalize()
 void comm_allreduce(double* buf, size_t count, int op)
 {
     if (!comm_active()) return;
+    if (p2p_active() && count <= 4) {
+        p2p_allreduce(buf, (int)count, op);
+        return;
+    }
     Ctx& c = ctx();
     ProfScope prof(401, (int)count, 0, 8.0 * count);
     nccl_check(N().AllReduce(buf, buf, count, ncclDouble, op == 2 ? ncclMax : ncclSum, N().comm, c.stream),
@@ -120,6 +127,7 @@ void comm_allgatherv(const double* send, size_t sendcount, double* recv, const s
                                     c.stream));
         return;
     }
+    if (send == recv + displs[n.rank] && p2p_allgatherv(recv, counts, displs)) return;
     // variable counts: one broadcast per root inside a group (fused by NCCL into one launch)
     ProfScope prof(402, (int)sendcount, 0, 8.0 * sendcount);
     nccl_check(n.GroupStart(), "ncclGroupStart");

@@ -147,6 +147,7 @@ struct DevCSR {
     double*   dinv = nullptr;     // 1/diag (first stored diagonal entry), poly smoother
     size_t    bytes = 0;
     bool      dup_diag = false;   // some row stores more than one (i,i) entry
+    int       vec_cap = 0;        // multi-GPU: entries a gathered vector holds (uniform over the ranks)
     int       nghost = 0;         // multi-GPU: ghost entries behind the owned part of a gathered vector
     HaloPlan* halo = nullptr;     // multi-GPU: ghosts of the gathered vector are exchanged before the kernel
 };
@@ -252,6 +253,7 @@ void flush_l2();
 // CUDA-graph capture of a fixed kernel sequence issued on ctx().stream
 // ------------------------------------------------------------------------------------
 namespace fc {
+void p2p_reset_order_hook();   // p2p.cu: a captured graph must not assume which vector was exchanged last
 struct CapturedGraph {
     cudaGraph_t     graph   = nullptr;
     cudaGraphExec_t exec    = nullptr;
@@ -274,6 +276,7 @@ struct CapturedGraph {
             return;
         }
         if (!exec) {
+            p2p_reset_order_hook();
             c.capturing = true;
             c.captured  = 0;
             cudaError_t e = cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal);

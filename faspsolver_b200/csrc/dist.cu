@@ -16,6 +16,7 @@
 // also makes the partition logic testable without GPUs (tests/test_dist_cpu.py).
 #include "dist.cuh"
 #include "comm.cuh"
+#include "p2p.cuh"
 #include <algorithm>
 
 namespace fc {
@@ -35,7 +36,9 @@ __global__ void k_halo_pack(int n, const int* __restrict__ idx, const double* __
 
 void halo_exchange(const HaloPlan& h, double* x)
 {
-    if (!comm_active() || (h.nsend == 0 && h.nghost == 0)) return;
+    if (!comm_active()) return;
+    if (p2p_halo_exchange(h, x)) return;   // peer-memory push + device barrier
+    if (h.nsend == 0 && h.nghost == 0) return;
     ProfScope prof(400, h.nloc, h.nsend + h.nghost, 8.0 * (h.nsend + h.nghost));
     if (h.nsend > 0) {
         int g = (h.nsend + 255) / 256;
@@ -165,6 +168,22 @@ static HaloPlan* make_plan(const dCSRmat& A, const std::vector<int>& roff, const
                                 ctx().stream));
         FC_CUDA(cudaStreamSynchronize(ctx().stream));
     }
+    if (p2p_active()) {
+        // tell every owner where its entries land behind my owned part: all-gather the receive
+        // offsets (collective; every rank builds its plans in the same order)
+        const int        nr = comm_size();
+        std::vector<int> mine(nr, -1), all;
+        for (size_t p = 0; p < h->recv_peer.size(); ++p) mine[h->recv_peer[p]] = h->recv_off[p];
+        p2p_allgather_ints(mine, all);
+        h->peer_dst_off.clear();
+        for (size_t k = 0; k < h->send_peer.size(); ++k) {
+            const int q   = h->send_peer[k];
+            const int off = all[(size_t)q * nr + rank];
+            if (off < 0) fail(ERROR_DATA_STRUCTURE, "halo plans of ranks %d and %d disagree", rank, q);
+            h->peer_dst_off.push_back((coff[q + 1] - coff[q]) + off);
+        }
+        h->p2p_ready = true;
+    }
     return h;
 }
 
@@ -255,7 +274,29 @@ Amg* dist_amg_upload(AMG_data* mgl, AMG_param* param, int agg_rows)
                     amg_level_smoother_data(*h, L, &A);
                 }
             }
+            if (comm_active() && (l <= lrep)) {
+                // identical vector capacity on every rank (peer addresses = same offsets)
+                double  c  = (double)(L.cap > L.n ? L.cap : L.n);
+                double* dc = dalloc<double>(1);
+                FC_CUDA(cudaMemcpyAsync(dc, &c, 8, cudaMemcpyHostToDevice, ctx().stream));
+                comm_allreduce(dc, 1, 2);
+                FC_CUDA(cudaMemcpyAsync(&c, dc, 8, cudaMemcpyDeviceToHost, ctx().stream));
+                FC_CUDA(cudaStreamSynchronize(ctx().stream));
+                dfree(dc);
+                L.cap = (int)c;
+                if (l == 0) L.A.vec_cap = L.cap;
+            }
             amg_level_vectors(*h, L);
+            if (l <= lrep) {   // partitioned levels + the first replicated one (all-gather target)
+                const size_t bytes = sizeof(double) * ((size_t)L.cap + 8);
+                p2p_register(L.b, bytes);
+                p2p_register(L.xa, bytes);
+                p2p_register(L.xb, bytes);
+                p2p_register(L.w, bytes);
+                for (int i = 0; i < 3; ++i)
+                    if (L.pv[i]) p2p_register(L.pv[i], bytes);
+                L.p2p_registered = true;
+            }
             h->bytes += L.A.bytes + L.P.bytes + L.R.bytes;
         }
         h->scal = dalloc<double>(4);

@@ -15,6 +15,9 @@ struct HaloPlan {
     int*    send_idx = nullptr;   // device: local indices to pack, all peers concatenated
     double* send_buf = nullptr;   // device: packed entries
     int     nsend    = 0;
+    // peer-memory path (p2p.cu): where each send segment lands inside the peer's vector
+    bool             p2p_ready = false;
+    std::vector<int> peer_dst_off;
 };
 void halo_free(HaloPlan* h);
 

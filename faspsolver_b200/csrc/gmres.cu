@@ -15,6 +15,7 @@
 #include "krylov.cuh"
 #include "reduce.cuh"
 #include "comm.cuh"
+#include "p2p.cuh"
 
 namespace fc {
 
@@ -308,6 +309,7 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
         if (t1) cudaEventDestroy(t1);
         if (pin_h) cudaFreeHost(pin_h);
         dfree(pin_d);
+        if (work && p2p_active()) p2p_unregister(work);
         dfree(work);
         dfree(st);
     };
@@ -316,6 +318,7 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
         // basis p[0..R], w, r ; hh (R+1) x R, c, s, rs ; norms + absres history
         const size_t nsmall = (size_t)(R + 1) * R + 2 * (size_t)R + (R + 1) + 2 * (size_t)hcap;
         work       = dalloc<double>((size_t)(R + 3) * ldp + nsmall);
+        if (p2p_active()) p2p_register(work, sizeof(double) * ((size_t)(R + 3) * ldp + nsmall));
         double* P  = work;
         double* w  = P + (size_t)(R + 1) * ldp;
         double* r  = w + ldp;

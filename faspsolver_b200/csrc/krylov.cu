@@ -14,6 +14,7 @@
 #include "krylov.cuh"
 #include "reduce.cuh"
 #include "comm.cuh"
+#include "p2p.cuh"
 
 namespace fc {
 
@@ -302,6 +303,8 @@ void PcgCache::release()
     t0 = t1 = nullptr;
     if (pin) cudaFreeHost(pin);
     pin = nullptr;
+    if (registered && work) p2p_unregister(work);
+    registered = false;
     dfree(work);
     dfree(st);
     work = nullptr;
@@ -333,6 +336,10 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
         W.release();
         W.work = dalloc<double>(4 * ncap + 3 * (size_t)hcap);
         W.ncap = ncap;
+        if (p2p_active()) {   // the search direction p is gathered by the peers' level-0 kernels
+            p2p_register(W.work, sizeof(double) * (4 * ncap + 3 * (size_t)hcap));
+            W.registered = true;
+        }
         W.st   = static_cast<void*>(dalloc<PcgState>(1));
         FC_CUDA(cudaMallocHost(&W.pin, sizeof(int) * 4 * (look + 1)));
         W.ev.resize(look + 1);

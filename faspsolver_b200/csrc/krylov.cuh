@@ -19,7 +19,10 @@ struct CsrOp : LinOp {
     const DevCSR* A;
     explicit CsrOp(const DevCSR* a) : A(a) { n = a->rows; }
     const void* key() const override { return A; }
-    size_t      vec_capacity() const override { return (size_t)A->rows + (size_t)A->nghost; }
+    size_t      vec_capacity() const override
+    {
+        return A->vec_cap > 0 ? (size_t)A->vec_cap : (size_t)A->rows + (size_t)A->nghost;
+    }
     void apply(int mode, double alpha, const double* x, const double* b, double* y,
                const Reduce& red, const int* done, bool conditional = false) override
     {
@@ -117,6 +120,7 @@ struct PcgCache {
     void*   st   = nullptr;
     int*    pin  = nullptr;
     size_t  n    = 0, ncap = 0;
+    bool    registered = false;   // work is peer-mapped (multi-GPU)
     int     hcap = 0, look = 0;
     std::vector<cudaEvent_t> ev;
     cudaEvent_t   t0 = nullptr, t1 = nullptr;

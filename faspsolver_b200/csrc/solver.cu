@@ -4,6 +4,8 @@
 // AMG-as-solver loop fasp_amg_solve (PreMGSolve.c:49-135).
 #include "solver.cuh"
 #include "reduce.cuh"
+#include "p2p.cuh"
+#include "comm.cuh"
 #include <thread>
 #include <chrono>
 
@@ -62,6 +64,10 @@ fasp_cuda_solver_s* solver_create_dist(AMG_data* mgl, AMG_param* amgparam, int a
         const size_t cap = (size_t)s->amg->lv[0].cap + 8;      // + ghosts of the level-0 operator
         s->d_b      = dalloc<double>(cap);
         s->d_x      = dalloc<double>(cap);
+        if (p2p_active()) {   // x is gathered by the peers when the true residual is formed
+            p2p_register(s->d_x, sizeof(double) * cap);
+            s->x_registered = true;
+        }
         FC_CUDA(cudaMallocHost(&s->pin, sizeof(double) * 2 * s->n));
     } catch (...) {
         solver_destroy(s);
@@ -92,6 +98,8 @@ fasp_cuda_solver_s* solver_create_bsr(AMG_data_bsr* mgl, AMG_param* amgparam)
 void solver_destroy(fasp_cuda_solver_s* s)
 {
     if (!s) return;
+    s->pcg_cache.release();
+    if (s->x_registered) p2p_unregister(s->d_x);
     amg_free(s->amg);
     bamg_free(s->bamg);
     dfree(s->d_b);
@@ -124,9 +132,12 @@ int solver_solve_dev(fasp_cuda_solver_s* s, const double* b_dev, double* x_dev, 
 {
     if (!s || (!s->amg && !s->bamg)) fail(ERROR_INPUT_PAR, "null solver");
     if (s->amg) {
-        CsrOp   op(&s->amg->lv[0].A);
-        AmgPrec pc(s->amg);
-        return run_krylov(s, op, pc, b_dev, x_dev, it);
+        CsrOp     op(&s->amg->lv[0].A);
+        AmgPrec   pc(s->amg);
+        const int ret = run_krylov(s, op, pc, b_dev, x_dev, it);
+        if (p2p_active() && p2p_error())
+            fail(ERROR_SOLVER_MISC, "multi-GPU barrier timed out (a rank fell out of step)");
+        return ret;
     }
     BsrOp    op(&s->bamg->lv[0].A);
     BAmgPrec pc(s->bamg);

@@ -16,6 +16,7 @@ struct fasp_cuda_solver_s {
     double*        d_x = nullptr;
     double*        pin = nullptr;      // pinned host staging (2n)
     size_t         n   = 0;
+    bool           x_registered = false;   // d_x is peer-mapped (multi-GPU)
 };
 
 namespace fc {

@@ -74,7 +74,7 @@ def barrier():
 class DistSolver(api.KrylovAmgSolver):
     """Row-partitioned solver: b / x are this rank's local slices (rows [row0, row1))."""
 
-    def __init__(self, mgl, amgparam, agg_rows=200_000):
+    def __init__(self, mgl, amgparam, agg_rows=8000):
         L = api.lib()
         self.h = L.fasp_cuda_dist_krylov_amg_create(mgl, C.byref(amgparam), int(agg_rows))
         if not self.h:
