@@ -136,6 +136,31 @@ def bench_main(args):
     launches = int(L.fasp_cuda_launch_count())
     clocks = sampler.stop()
     barrier()
+    # roofline of the dominant kernel on this rank's slab: CUDA events around every launch of one
+    # more solve (graphs off); level-0 local matrix = the largest (rows, nnz) record
+    L.fasp_cuda_set_option(b"profile", 1.0)
+    L.fasp_cuda_profile_dump(None, 0)
+    host_solve()
+    buf = C.create_string_buffer(64 << 20)
+    L.fasp_cuda_profile_dump(buf, len(buf))
+    L.fasp_cuda_set_option(b"profile", 0.0)
+    recs = [ln.split() for ln in buf.value.decode().splitlines()]
+    recs = [(int(k), int(r), int(z_), float(ms_), float(by)) for k, r, z_, ms_, by in recs]
+    mat = [r for r in recs if r[0] < 50 and r[1] == nloc]
+    roofline = None
+    if mat:
+        top = max(r[2] for r in mat)
+        l0 = [r for r in mat if r[2] == top]
+        med = float(np.median([r[3] for r in l0]))
+        l0 = [r for r in l0 if r[3] >= 0.25 * med]
+        t_ms = sum(r[3] for r in l0)
+        ach = sum(r[4] for r in l0) / t_ms * 1e-6
+        peak, src = B.peaks()
+        comm_ms = sum(r[3] for r in recs if r[0] >= 400)
+        roofline = {"bound": "hbm", "kernel": "csr_pipe_kernel on rank 0's level-0 slab (%d rows, %d nnz)" % (nloc, top),
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": src, "launch_ms": t_ms / len(l0),
+                    "comm_ms_per_solve_profiled": comm_ms, "comm_ops_per_solve": len([r for r in recs if r[0] >= 400])}
     # true residual of the assembled solution (rank 0)
     import torch
     import torch.distributed as dist
@@ -163,7 +188,7 @@ def bench_main(args):
             "e2e": {"value": float(np.mean(e2e_ms)), "unit": B.UNIT, "h2d_bytes_per_step": int(16 * nloc),
                     "d2h_bytes_per_step": int(8 * nloc)},
             "gpu_launches": launches, "clocks": clocks,
-            "roofline": None, "cpu_baseline": None,
+            "roofline": roofline, "cpu_baseline": None,
         }
     solver.close()
     L.fasp_cuda_comm_finalize()
