@@ -160,6 +160,8 @@ static int* option_slot(const char* key)
     if (!strcmp(key, "pipe_ctas")) return &o.pipe_ctas;
     if (!strcmp(key, "pipe_stages")) return &o.pipe_stages;
     if (!strcmp(key, "pipe_tpb")) return &o.pipe_tpb;
+    if (!strcmp(key, "pipe_cap_mult")) return &o.pipe_cap_mult;
+    if (!strcmp(key, "sort_rows")) return &o.sort_rows;
     if (!strcmp(key, "rowwise_max")) return &o.rowwise_max;
     if (!strcmp(key, "vec_lpr")) return &o.vec_lpr;
     if (!strcmp(key, "gs_multicolor")) return &o.gs_multicolor;

@@ -21,6 +21,8 @@
 #include "common.cuh"
 #include "reduce.cuh"
 #include "pipe.cuh"
+#include <algorithm>
+#include <thread>
 
 namespace fc {
 
@@ -127,177 +129,12 @@ __device__ __forceinline__ void cp_async_wait_all()
 }
 
 // ------------------------------------------------------------------------------------
-// kernel S ("stream"): one CTA per row block, products parked in shared memory
-// ------------------------------------------------------------------------------------
-template <int MODE, bool PATTERN>
-__global__ void __launch_bounds__(TPB)
-csr_rowblock_kernel(const CsrView A, const CsrArgs a, const int strict, double* partials,
-                    unsigned int* ticket)
-{
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ double s_red[2][TPB / 32];
-
-    if (a.done != nullptr && *a.done != 0) return;
-
-    double* s_prod = reinterpret_cast<double*>(s_raw);              // cap + 8 entries
-    int*    s_ja   = reinterpret_cast<int*>(s_prod + A.cap + 8);    // cap + 8 entries
-
-    const int tid   = threadIdx.x;
-    const int r0    = A.rowblk[blockIdx.x];
-    const int r1    = A.rowblk[blockIdx.x + 1];
-    const int nrows = r1 - r0;
-    const int k0    = A.ia[r0];
-    const int n     = A.ia[r1] - k0;
-    const double* __restrict__ x = a.x;
-
-    double red_dot = 0.0, red_n2 = 0.0;
-    const bool want_dot = a.red.dot_out != nullptr;
-    const bool want_n2  = a.red.nrm2_out != nullptr;
-
-    if (n <= A.cap) {
-        // ---- phase 1a: asynchronous bulk staging of the block's ja / val slice. The slice is
-        // widened to 4-entry (16 B / 32 B) boundaries; the arrays are padded by 8 entries.
-        const int k0a = k0 & ~3;
-        const int d   = k0 - k0a;
-        const int na  = ((k0 + n + 3) & ~3) - k0a;
-        {
-            const int* gja = A.ja + k0a;
-            for (int c = tid; c < (na >> 2); c += TPB) cp_async16(s_ja + 4 * c, gja + 4 * c);
-            if (!PATTERN) {
-                const double* gval = A.val + k0a;
-                for (int c = tid; c < (na >> 1); c += TPB) cp_async16(s_prod + 2 * c, gval + 2 * c);
-            }
-            cp_async_wait_all();
-        }
-        __syncthreads();
-        // ---- phase 1b: gather x and form the products in place
-        double*    sp = s_prod + d;
-        const int* sj = s_ja + d;
-        // (indices first, then all gathers, then the products: a store to shared memory
-        // between two gathers would serialise them on the L2 latency)
-        {
-            constexpr int EPT = CAP_MAX / TPB;   // entries per thread, cap <= CAP_MAX
-            int           col[EPT];
-            double        xv[EPT];
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) {
-                const int k = tid + e * TPB;
-                col[e]      = (k < n) ? sj[k] : -1;
-            }
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) xv[e] = (col[e] >= 0) ? __ldg(x + col[e]) : 0.0;
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) {
-                const int k = tid + e * TPB;
-                if (k < n) sp[k] = PATTERN ? xv[e] : __dmul_rn(sp[k], xv[e]);
-            }
-        }
-        __syncthreads();
-
-        // ---- phase 2: rows
-        // lanes per row: 1 while rows average <= 32 nonzeros (exact CPU order), then one
-        // lane per ~32 nonzeros as far as the CTA has threads for it
-        int lpr = 1;
-        if (!strict)
-            while (lpr < 32 && nrows * lpr * 2 <= TPB && n > 32 * lpr * nrows) lpr <<= 1;
-
-        if (lpr == 1) {
-            if (tid < nrows) {
-                const int row = r0 + tid;
-                const int ka  = A.ia[row] - k0;
-                const int kb  = A.ia[row + 1] - k0;
-                double    acc;
-                if (ModeTraits<MODE>::smoother) {
-                    acc            = a.b[row];
-                    const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
-                    for (int k = ka; k < kb; ++k)
-                        if (k != skip) acc = __dsub_rn(acc, sp[k]);
-                } else {
-                    acc = 0.0;
-                    for (int k = ka; k < kb; ++k) acc = __dadd_rn(acc, sp[k]);
-                }
-                const double out = row_epilogue<MODE>(A, a, row, acc, true);
-                if (want_dot) red_dot = out * a.red.dot_with[row];
-                if (want_n2) red_n2 = out * out;
-            }
-        } else {
-            const int  g     = tid / lpr;
-            const int  gl    = tid - g * lpr;
-            const bool valid = g < nrows;
-            double     part  = 0.0;
-            int        row   = r0;
-            if (valid) {
-                row            = r0 + g;
-                const int ka   = A.ia[row] - k0;
-                const int kb   = A.ia[row + 1] - k0;
-                const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
-                for (int k = ka + gl; k < kb; k += lpr)
-                    if (k != skip) part += sp[k];
-            }
-            for (int off = lpr >> 1; off > 0; off >>= 1)
-                part += __shfl_xor_sync(0xffffffffu, part, off);
-            if (valid && gl == 0) {
-                const double out = row_epilogue<MODE>(A, a, row, part, false);
-                if (want_dot) red_dot = out * a.red.dot_with[row];
-                if (want_n2) red_n2 = out * out;
-            }
-        }
-    } else {
-        // ---- one row longer than the shared-memory capacity: whole CTA on it
-        const int row  = r0;
-        const int skip = ModeTraits<MODE>::skipdiag ? k0 + A.dpos[row] : -1;
-        if (strict) {
-            if (tid == 0) {
-                double acc = ModeTraits<MODE>::smoother ? a.b[row] : 0.0;
-                for (int k = k0; k < k0 + n; ++k) {
-                    if (k == skip) continue;
-                    const double p = PATTERN ? x[A.ja[k]] : __dmul_rn(A.val[k], x[A.ja[k]]);
-                    acc = ModeTraits<MODE>::smoother ? __dsub_rn(acc, p) : __dadd_rn(acc, p);
-                }
-                const double out = row_epilogue<MODE>(A, a, row, acc, true);
-                if (want_dot) red_dot = out * a.red.dot_with[row];
-                if (want_n2) red_n2 = out * out;
-            }
-        } else {
-            double part = 0.0;
-#pragma unroll 4
-            for (int k = k0 + tid; k < k0 + n; k += TPB) {
-                const double xv = __ldg(x + ld_stream_i32(A.ja + k));
-                const double p  = PATTERN ? xv : ld_stream_f64(A.val + k) * xv;
-                if (k != skip) part += p;
-            }
-            for (int off = 16; off > 0; off >>= 1)
-                part += __shfl_xor_sync(0xffffffffu, part, off);
-            if ((tid & 31) == 0) s_red[0][tid >> 5] = part;
-            __syncthreads();
-            if (tid == 0) {
-                double acc = 0.0;
-                for (int w = 0; w < TPB / 32; ++w) acc += s_red[0][w];
-                const double out = row_epilogue<MODE>(A, a, row, acc, false);
-                if (want_dot) red_dot = out * a.red.dot_with[row];
-                if (want_n2) red_n2 = out * out;
-            }
-            __syncthreads();
-        }
-    }
-
-    // ---- fused grid reduction (deterministic: partials are added in CTA order)
-    if (want_dot || want_n2) {
-        double v[2] = {red_dot, red_n2};
-        grid_reduce<2, 0>(v, partials, ticket, [&](const double* t) {
-            if (want_dot) *a.red.dot_out = t[0];
-            if (want_n2) *a.red.nrm2_out = t[1];
-        });
-    }
-}
-
-// ------------------------------------------------------------------------------------
 // kernel P ("pipelined stream"): persistent CTAs, TMA bulk copies (cp.async.bulk +
 // mbarrier) stage the ja / val / ia slices of the NEXT row blocks into a ring of shared-
 // memory stages while the current block is gathered and reduced. The streamed bytes in
 // flight per SM are (stages - 1) x slice x CTAs/SM, independent of registers and occupancy;
 // the only latency left on a block's critical path is the x gather (L1/L2).
-// Same per-row arithmetic as kernel S (one thread per short row: exact CPU order).
+// One thread per short row: exact CPU summation order.
 // ------------------------------------------------------------------------------------
 constexpr int P_MAX_STAGES = 8;
 constexpr int P_EPT = 8;            // entries per thread and stage: cap <= P_EPT * threads
@@ -315,7 +152,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
     __shared__ __align__(8) unsigned long long s_bar[P_MAX_STAGES];
     __shared__ PipeMeta s_meta[P_MAX_STAGES];
     __shared__ double   s_red[T / 32];
-    constexpr int EPT = P_EPT;   // cap <= P_EPT * T
+    constexpr int EPT = P_EPT;   // gathers in flight per thread in the entry-wise path
 
     if (a.done != nullptr && *a.done != 0) return;
 
@@ -410,19 +247,19 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
             } else {
                 // ---- longer rows: entry-wise gather, products parked in the stage, then a
                 // group of lpr lanes per row adds them
-                {
+                for (int base = 0; base < n; base += EPT * T) {
                     int    col[EPT];
                     double xv[EPT];
 #pragma unroll
                     for (int e = 0; e < EPT; ++e) {
-                        const int k = tid + e * T;
+                        const int k = base + tid + e * T;
                         col[e]      = (k < n) ? sj[k] : -1;
                     }
 #pragma unroll
                     for (int e = 0; e < EPT; ++e) xv[e] = (col[e] >= 0) ? __ldg(x + col[e]) : 0.0;
 #pragma unroll
                     for (int e = 0; e < EPT; ++e) {
-                        const int k = tid + e * T;
+                        const int k = base + tid + e * T;
                         if (k < n) sp[k] = PATTERN ? xv[e] : __dmul_rn(sp[k], xv[e]);
                     }
                 }
@@ -633,15 +470,11 @@ static void launch_pattern(const DevCSR& A, const CsrView& v, const CsrArgs& a)
         part = red_partials((size_t)A.nblk);
         tick = red_ticket();
     }
-    if (c.opt.pipe) {
-        switch (A.blk_tpb) {
-            case 64: launch_pipe<MODE, PATTERN, 64>(A, v, a, part, tick); return;
-            case 128: launch_pipe<MODE, PATTERN, 128>(A, v, a, part, tick); return;
-            default: launch_pipe<MODE, PATTERN, 256>(A, v, a, part, tick); return;
-        }
+    switch (A.blk_tpb) {
+        case 64: launch_pipe<MODE, PATTERN, 64>(A, v, a, part, tick); return;
+        case 128: launch_pipe<MODE, PATTERN, 128>(A, v, a, part, tick); return;
+        default: launch_pipe<MODE, PATTERN, 256>(A, v, a, part, tick); return;
     }
-    const size_t smem = (size_t)(A.blk_cap + 8) * (sizeof(double) + sizeof(int));
-    FC_LAUNCH((csr_rowblock_kernel<MODE, PATTERN>), A.nblk, TPB, smem, v, a, c.opt.strict, part, tick);
 }
 
 template <int MODE>
@@ -776,6 +609,46 @@ void csr_upload(DevCSR& d, int rows, int cols, long long nnz, const int* ia, con
     d.nnz  = nnz;
     if (nnz >= 2147483647LL) fail(ERROR_MAT_SIZE, "csr_upload: nnz exceeds 32-bit offsets");
     const size_t pad = 8;
+    // kernel choice: short rows -> pipelined stream kernel (exact CPU summation order); longer
+    // rows -> vector kernel with LPR lanes per row
+    const double avg0 = rows > 0 ? (double)nnz / rows : 1.0;
+    d.vec_lpr         = 0;
+    const int vmin    = c.opt.vec_min_avg;
+    if (vmin > 0 && avg0 >= vmin)
+        d.vec_lpr = c.opt.vec_lpr > 0 ? c.opt.vec_lpr : (avg0 < 48 ? 4 : (avg0 < 96 ? 8 : (avg0 < 384 ? 16 : 32)));
+    // Rows that go to the vector kernel are summed by lane groups anyway (order differs from the
+    // CPU loop by construction), so their entries are sorted by column at upload: consecutive lanes
+    // then gather neighbouring x entries and share 32-byte sectors (the unsorted RAP output of
+    // the host setup scatters them). Short rows keep FASP's storage order = the CPU summation order.
+    std::vector<int>    sja;
+    std::vector<double> sval;
+    if (d.vec_lpr > 0 && c.opt.sort_rows && !c.opt.strict && nnz > 0) {
+        sja.assign(ja, ja + nnz);
+        if (!pattern_only && val) sval.assign(val, val + nnz);
+        const unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&, t]() {
+                std::vector<std::pair<int, double>> tmp;
+                for (int i = (int)(((long long)rows * t) / nt); i < (int)(((long long)rows * (t + 1)) / nt); ++i) {
+                    const int a = ia[i], b = ia[i + 1];
+                    if (b - a < 2 || std::is_sorted(sja.begin() + a, sja.begin() + b)) continue;
+                    tmp.resize(b - a);
+                    for (int k = a; k < b; ++k) tmp[k - a] = {sja[k], sval.empty() ? 0.0 : sval[k]};
+                    std::stable_sort(tmp.begin(), tmp.end(),
+                                     [](const std::pair<int, double>& x, const std::pair<int, double>& y) {
+                                         return x.first < y.first;
+                                     });
+                    for (int k = a; k < b; ++k) {
+                        sja[k] = tmp[k - a].first;
+                        if (!sval.empty()) sval[k] = tmp[k - a].second;
+                    }
+                }
+            });
+        for (auto& t : th) t.join();
+        ja = sja.data();
+        if (!sval.empty()) val = sval.data();
+    }
     d.ia             = dalloc<int>((size_t)rows + 1 + pad);
     FC_CUDA(cudaMemsetAsync(d.ia + rows + 1, 0, sizeof(int) * pad, c.stream));
     d.ja             = dalloc<int>((size_t)nnz + pad);
@@ -792,6 +665,7 @@ void csr_upload(DevCSR& d, int rows, int cols, long long nnz, const int* ia, con
         FC_CUDA(cudaMemsetAsync(d.val + nnz, 0, sizeof(double) * pad, c.stream));
         d.bytes += sizeof(double) * ((size_t)nnz + pad);
     }
+    FC_CUDA(cudaStreamSynchronize(c.stream));   // sorted staging copies go out of scope below
     // row blocks: at most T rows (T = threads of the pipelined kernel) and cap products, cap ~ T
     // average rows and <= 8 T (12 B of shared memory per product and stage)
     const double avg = rows > 0 ? (double)nnz / rows : 1.0;
@@ -800,13 +674,11 @@ void csr_upload(DevCSR& d, int rows, int cols, long long nnz, const int* ia, con
     d.blk_tpb     = T;
     long long cap = (long long)(avg * T + 63) / 64 * 64;
     if (cap < 4 * T) cap = 4 * T;
-    if (cap > P_EPT * T) cap = P_EPT * T;
+    int mult = c.opt.pipe_cap_mult;
+    if (mult < 4) mult = 4;
+    if (mult > 32) mult = 32;
+    if (cap > (long long)mult * T) cap = (long long)mult * T;
     d.blk_cap = (int)cap;
-    // kernel choice: short rows -> stream kernel (exact CPU summation order); longer rows ->
-    // vector kernel with LPR lanes per row
-    d.vec_lpr = 0;
-    const int vmin = c.opt.vec_min_avg;
-    if (vmin > 0 && avg >= vmin) d.vec_lpr = c.opt.vec_lpr > 0 ? c.opt.vec_lpr : (avg < 96 ? 8 : (avg < 384 ? 16 : 32));
     std::vector<int> rb;
     build_rowblocks(rows, ia, d.blk_cap, d.blk_tpb, rb);
     d.nblk   = (int)rb.size() - 1;
