@@ -201,8 +201,9 @@ def run_ours(args):
     # ---- e2e: host-pointer call, H2D(b, x0) + solve + D2H(x) inside the timed region
     e2e_times = []
     x_host = None
+    x_buf = np.zeros(n)
     for k in range(max(1, args.warmup // 2) + args.steps):
-        st, x_host = solver.solve(b, zero, it)
+        st, x_host = solver.solve(b, zero, it, out=x_buf)
         if st < 0:
             raise RuntimeError("host solve failed: %d %s" % (st, api.last_error()))
         if k >= max(1, args.warmup // 2):

@@ -288,8 +288,14 @@ class KrylovAmgSolver:
         if not self.h:
             raise FaspCudaError(-1, last_error())
 
-    def solve(self, b: np.ndarray, x0: np.ndarray, itparam: ITS_param):
-        vb, vx = Vec(b), Vec(np.array(x0, dtype=np.float64, copy=True))
+    def solve(self, b: np.ndarray, x0: np.ndarray, itparam: ITS_param, out: np.ndarray | None = None):
+        """x0 is not modified; the solution is returned in `out` when given (an application that solves
+        many systems re-uses its arrays, which lets the library keep them page-locked)."""
+        if out is None:
+            out = np.array(x0, dtype=np.float64, copy=True)
+        else:
+            out[:] = x0
+        vb, vx = Vec(b), Vec(out)
         st = lib().fasp_cuda_krylov_amg_solve(self.h, vb.ptr(), vx.ptr(), C.byref(itparam))
         return st, vx.a
 

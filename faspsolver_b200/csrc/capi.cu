@@ -162,6 +162,7 @@ static int* option_slot(const char* key)
     if (!strcmp(key, "pipe_tpb")) return &o.pipe_tpb;
     if (!strcmp(key, "pipe_cap_mult")) return &o.pipe_cap_mult;
     if (!strcmp(key, "sort_rows")) return &o.sort_rows;
+    if (!strcmp(key, "host_register")) return &o.host_register;
     if (!strcmp(key, "rowwise_max")) return &o.rowwise_max;
     if (!strcmp(key, "vec_lpr")) return &o.vec_lpr;
     if (!strcmp(key, "gs_multicolor")) return &o.gs_multicolor;

@@ -58,6 +58,7 @@ struct Options {
     int    pipe             = 1;   // stream kernel: persistent TMA-pipelined variant
     int    pipe_ctas        = 8;   // its CTAs per SM (upper bound)
     int    pipe_stages      = 2;   // its shared-memory stages per CTA
+    int    host_register    = 1;   // page-lock caller buffers in place for host-pointer solves
     int    sort_rows        = 1;   // sort the entries of vector-kernel rows by column at upload
     int    pipe_cap_mult    = 8;   // row-block capacity <= this many nonzeros per thread
     int    pipe_tpb         = 128; // its threads per CTA = max rows per row block (64/128/256)

@@ -98,6 +98,11 @@ fasp_cuda_solver_s* solver_create_bsr(AMG_data_bsr* mgl, AMG_param* amgparam)
 void solver_destroy(fasp_cuda_solver_s* s)
 {
     if (!s) return;
+    for (auto& r : s->hostreg) {
+        cudaHostUnregister(const_cast<void*>(r.p));
+        cudaGetLastError();
+    }
+    s->hostreg.clear();
     s->pcg_cache.release();
     if (s->x_registered) p2p_unregister(s->d_x);
     amg_free(s->amg);
@@ -150,15 +155,49 @@ int solver_solve_host(fasp_cuda_solver_s* s, const double* b, double* x, ITS_par
     Ctx&         c  = ctx();
     const size_t n  = s->n;
     const auto   w0 = std::chrono::steady_clock::now();
-    // pageable caller memory -> pinned staging -> HBM (and back)
-    par_memcpy(s->pin, b, sizeof(double) * n);
-    FC_CUDA(cudaMemcpyAsync(s->d_b, s->pin, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
-    par_memcpy(s->pin + n, x, sizeof(double) * n);   // overlaps the DMA of b
-    FC_CUDA(cudaMemcpyAsync(s->d_x, s->pin + n, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    // Caller buffers are page-locked in place the first time they are seen (cudaHostRegister is
+    // slow, so the registration is remembered: applications solve many right-hand sides with the
+    // same arrays); the copies are then plain DMA transfers. A buffer that cannot be registered
+    // goes through the pinned staging area instead.
+    const size_t bytes = sizeof(double) * n;
+    auto pinned = [&](const void* p) -> bool {
+        if (!ctx().opt.host_register) return false;
+        for (auto& r : s->hostreg)
+            if (r.p == p && r.bytes >= bytes) return true;
+        if (s->hostreg.size() >= 8) {
+            cudaHostUnregister(const_cast<void*>(s->hostreg.front().p));
+            cudaGetLastError();
+            s->hostreg.erase(s->hostreg.begin());
+        }
+        if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        s->hostreg.push_back({p, bytes});
+        return true;
+    };
+    const bool pb = pinned(b), px = pinned(x);
+    if (pb) {
+        FC_CUDA(cudaMemcpyAsync(s->d_b, b, bytes, cudaMemcpyHostToDevice, c.stream));
+    } else {
+        par_memcpy(s->pin, b, bytes);
+        FC_CUDA(cudaMemcpyAsync(s->d_b, s->pin, bytes, cudaMemcpyHostToDevice, c.stream));
+    }
+    if (px) {
+        FC_CUDA(cudaMemcpyAsync(s->d_x, x, bytes, cudaMemcpyHostToDevice, c.stream));
+    } else {
+        par_memcpy(s->pin + n, x, bytes);   // overlaps the DMA of b
+        FC_CUDA(cudaMemcpyAsync(s->d_x, s->pin + n, bytes, cudaMemcpyHostToDevice, c.stream));
+    }
     const int ret = solver_solve_dev(s, s->d_b, s->d_x, it);
-    FC_CUDA(cudaMemcpyAsync(s->pin + n, s->d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
-    FC_CUDA(cudaStreamSynchronize(c.stream));
-    par_memcpy(x, s->pin + n, sizeof(double) * n);
+    if (px) {
+        FC_CUDA(cudaMemcpyAsync(x, s->d_x, bytes, cudaMemcpyDeviceToHost, c.stream));
+        FC_CUDA(cudaStreamSynchronize(c.stream));
+    } else {
+        FC_CUDA(cudaMemcpyAsync(s->pin + n, s->d_x, bytes, cudaMemcpyDeviceToHost, c.stream));
+        FC_CUDA(cudaStreamSynchronize(c.stream));
+        par_memcpy(x, s->pin + n, bytes);
+    }
     // wall clock of the whole host-pointer call: staging, H2D, solve, D2H, un-staging
     s->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
     return ret;

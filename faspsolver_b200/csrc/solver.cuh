@@ -17,6 +17,9 @@ struct fasp_cuda_solver_s {
     double*        pin = nullptr;      // pinned host staging (2n)
     size_t         n   = 0;
     bool           x_registered = false;   // d_x is peer-mapped (multi-GPU)
+    // caller buffers page-locked in place (cudaHostRegister) and remembered across solves
+    struct HostReg { const void* p; size_t bytes; };
+    std::vector<HostReg> hostreg;
 };
 
 namespace fc {

@@ -115,8 +115,10 @@ def bench_main(args):
     zero = np.zeros(nloc)
     log("[bench] rank 0 owns rows [%d, %d) of %d; upload %.2fs" % (r0, r1, n, t_upload))
 
+    x_buf = np.zeros(nloc)
+
     def host_solve():
-        st, x = solver.solve(b_loc, zero, it)
+        st, x = solver.solve(b_loc, zero, it, out=x_buf)
         if st < 0:
             raise RuntimeError("solve failed on rank %d: %d %s" % (rank, st, api.last_error()))
         return st, x

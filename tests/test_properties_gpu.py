@@ -91,5 +91,5 @@ def test_amg_pcg_128_iterations_and_residual(gpu, ref):
         ref.amg_free(mgl, amg)
     assert st == 12, st
     assert abs(relres_reported - 1.3856055505e-09) / 1.3856055505e-09 < 1e-6
-    assert hist.size == 13 and np.all(np.diff(hist[1:]) < 0) and abs(hist[-1] - relres_reported) < 1e-20
+    assert hist.size == 13 and np.all(np.diff(hist[1:]) < 0) and abs(hist[-1] - relres_reported) < 1e-5 * relres_reported
     assert np.linalg.norm(b - A.to_scipy() @ x) / np.linalg.norm(b) <= 1e-8
