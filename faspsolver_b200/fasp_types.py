@@ -163,7 +163,9 @@ class CSR:
         return int(self.ia[-1])
 
     def ptr(self):
-        return C.byref(self.struct)
+        p = C.pointer(self.struct)
+        p._owner = self   # the pointer keeps the numpy arrays alive (safe with temporaries)
+        return p
 
     def to_scipy(self):
         import scipy.sparse as sp
@@ -204,7 +206,9 @@ class BSR:
         return int(self.ia[-1])
 
     def ptr(self):
-        return C.byref(self.struct)
+        p = C.pointer(self.struct)
+        p._owner = self   # the pointer keeps the numpy arrays alive (safe with temporaries)
+        return p
 
     def to_scipy(self):
         import scipy.sparse as sp
@@ -218,7 +222,9 @@ class Vec:
         self.struct = dvector(int(self.a.size), self.a.ctypes.data_as(PREAL))
 
     def ptr(self):
-        return C.byref(self.struct)
+        p = C.pointer(self.struct)
+        p._owner = self   # the pointer keeps the numpy arrays alive (safe with temporaries)
+        return p
 
 
 def as_preal(a: np.ndarray):
