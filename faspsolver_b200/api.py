@@ -94,6 +94,8 @@ def lib():
         "fasp_cuda_solver_dcsr_pcg": (INT, [P(dCSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT]),
         "fasp_cuda_solver_dcsr_pvgmres": (INT, [P(dCSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT, SHORT]),
         "fasp_cuda_solver_dcsr_pgmres": (INT, [P(dCSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT, SHORT]),
+        "fasp_cuda_solver_dcsr_pvfgmres": (INT, [P(dCSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT, SHORT]),
+        "fasp_cuda_solver_dbsr_pvfgmres": (INT, [P(dBSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT, SHORT]),
         "fasp_cuda_solver_dbsr_pcg": (INT, [P(dBSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT]),
         "fasp_cuda_solver_dbsr_pvgmres": (INT, [P(dBSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT, SHORT]),
         "fasp_cuda_solver_dbsr_pgmres": (INT, [P(dBSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT, SHORT]),

@@ -775,6 +775,26 @@ INT fasp_cuda_solver_dcsr_pvgmres(dCSRmat* A, dvector* b, dvector* x, precond* p
     API_CATCH(code__)
 }
 
+INT fasp_cuda_solver_dcsr_pvfgmres(dCSRmat* A, dvector* b, dvector* x, precond* pc,
+                                   const REAL tol, const REAL abstol, const INT MaxIt,
+                                   const SHORT restart, const SHORT StopType, const SHORT PrtLvl)
+{
+    API_TRY
+    ensure_init();
+    check_csr(A);
+    const size_t n = b->row;
+    TmpCSR       dA(A);
+    CsrOp        op(&dA.m);
+    DVec         db(b->val, n), dx(x->val, n);
+    PrecChoice   pch;
+    choose_prec(pch, pc, n);
+    const int ret = gmres_solve(op, db.p, dx.p, *pch.p, tol, abstol, MaxIt, restart, StopType,
+                                PrtLvl, GM_FLEXIBLE, nullptr);
+    dx.to_host(x->val);
+    return ret;
+    API_CATCH(code__)
+}
+
 INT fasp_cuda_solver_dcsr_pgmres(dCSRmat* A, dvector* b, dvector* x, precond* pc, const REAL tol,
                                  const REAL abstol, const INT MaxIt, const SHORT restart,
                                  const SHORT StopType, const SHORT PrtLvl)
@@ -808,8 +828,10 @@ INT fasp_cuda_solver_dcsr_itsolver(dCSRmat* A, dvector* b, dvector* x, precond* 
             return fasp_cuda_solver_dcsr_pgmres(A, b, x, pc, tol, abstol, maxit, (SHORT)restart, stop, prt);
         case SOLVER_VGMRES:
             return fasp_cuda_solver_dcsr_pvgmres(A, b, x, pc, tol, abstol, maxit, (SHORT)restart, stop, prt);
+        case SOLVER_VFGMRES:
+            return fasp_cuda_solver_dcsr_pvfgmres(A, b, x, pc, tol, abstol, maxit, (SHORT)restart, stop, prt);
         default:
-            set_last_error("itsolver_type not on the device path (supported: CG 1, GMRES 4, VGMRES 5)");
+            set_last_error("itsolver_type not on the device path (supported: CG 1, GMRES 4, VGMRES 5, VFGMRES 6)");
             return ERROR_SOLVER_TYPE;
     }
 }
@@ -952,7 +974,8 @@ int bsr_krylov_host(dBSRmat* A, dvector* b, dvector* x, precond* pc, double tol,
     else pch.p = new HostPrec(pc, n);
     int ret;
     if (which == 0) ret = pcg_solve(op, db.p, dx.p, *pch.p, tol, abstol, MaxIt, StopType, PrtLvl, nullptr);
-    else ret = gmres_solve(op, db.p, dx.p, *pch.p, tol, abstol, MaxIt, restart, StopType, PrtLvl, which == 2, nullptr);
+    else ret = gmres_solve(op, db.p, dx.p, *pch.p, tol, abstol, MaxIt, restart, StopType, PrtLvl,
+                           which == 3 ? GM_FLEXIBLE : (which == 2 ? GM_VARIABLE : GM_FIXED), nullptr);
     dx.to_host(x->val);
     return ret;
 }
@@ -1127,6 +1150,13 @@ INT fasp_cuda_solver_dbsr_pvgmres(dBSRmat* A, dvector* b, dvector* x, precond* p
     return bsr_krylov_host(A, b, x, pc, tol, abstol, MaxIt, restart, StopType, PrtLvl, 2);
     API_CATCH(code__)
 }
+INT fasp_cuda_solver_dbsr_pvfgmres(dBSRmat* A, dvector* b, dvector* x, precond* pc, const REAL tol, const REAL abstol,
+                                   const INT MaxIt, const SHORT restart, const SHORT StopType, const SHORT PrtLvl)
+{
+    API_TRY
+    return bsr_krylov_host(A, b, x, pc, tol, abstol, MaxIt, restart, StopType, PrtLvl, 3);
+    API_CATCH(code__)
+}
 INT fasp_cuda_solver_dbsr_itsolver(dBSRmat* A, dvector* b, dvector* x, precond* pc, ITS_param* itparam)
 {
     // SolBSR.c:55-140
@@ -1137,8 +1167,9 @@ INT fasp_cuda_solver_dbsr_itsolver(dBSRmat* A, dvector* b, dvector* x, precond* 
         case SOLVER_CG: return fasp_cuda_solver_dbsr_pcg(A, b, x, pc, tol, abstol, maxit, stop, prt);
         case SOLVER_GMRES: return fasp_cuda_solver_dbsr_pgmres(A, b, x, pc, tol, abstol, maxit, (SHORT)restart, stop, prt);
         case SOLVER_VGMRES: return fasp_cuda_solver_dbsr_pvgmres(A, b, x, pc, tol, abstol, maxit, (SHORT)restart, stop, prt);
+        case SOLVER_VFGMRES: return fasp_cuda_solver_dbsr_pvfgmres(A, b, x, pc, tol, abstol, maxit, (SHORT)restart, stop, prt);
         default:
-            set_last_error("itsolver_type not on the device path (supported: CG 1, GMRES 4, VGMRES 5)");
+            set_last_error("itsolver_type not on the device path (supported: CG 1, GMRES 4, VGMRES 5, VFGMRES 6)");
             return ERROR_SOLVER_TYPE;
     }
 }

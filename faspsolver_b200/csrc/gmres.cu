@@ -1,6 +1,8 @@
 // gmres.cu — right-preconditioned restarted GMRES on the device: fixed restart
-// (fasp_solver_dcsr_pgmres, KryPgmres.c:66) and variable restart (fasp_solver_dcsr_pvgmres,
-// KryPvgmres.c:66-387, Baker/Jessup/Kolev adaptation :200-210); BSR twins share the code.
+// (fasp_solver_dcsr_pgmres, KryPgmres.c:66), variable restart (fasp_solver_dcsr_pvgmres,
+// KryPvgmres.c:66-387, Baker/Jessup/Kolev adaptation :200-210) and the flexible variant
+// (fasp_solver_dcsr_pvfgmres, KryPvfgmres.c:67-358: keeps z_j = B p_j, stops on the absolute
+// residual against tol * ||b||); BSR twins share the code.
 //
 // Device residency: basis vectors, Hessenberg matrix, Givens rotations, rs[] and all
 // norms live in HBM. Inside a restart cycle nothing returns to the host: every inner step is
@@ -22,8 +24,9 @@ namespace fc {
 struct GmState {
     double r_norm, r_norm_old, absres0, absres, relres, normu, cr, tol, abstol;
     double rr, t2, xx, scale;
-    int    iter, maxit, i, stop_type, variable;
-    int    done, converged;
+    double den_norm, epsilon;   // flexible variant: ||b|| (or ||r0||) and tol * den_norm
+    int    iter, maxit, i, stop_type, variable, flexible;
+    int    done, converged, silent;
     int    skip_inner, skip_scale, skip_true, skip_copy;
     int    R;   // leading dimension of hh: hh[j][k] = H[j * R + k]
 };
@@ -34,9 +37,24 @@ struct GmPinned {
 };
 
 // p0 = b - A x done; rr = ||p0||^2, xx = ||x||^2 (MOD only)     (KryPvgmres.c:149-182)
-__global__ void k_gm_init(GmState* st, double* norms)
+__global__ void k_gm_init(GmState* st, double* norms, double* habs)
 {
     st->r_norm = sqrt(st->rr);
+    if (st->flexible) {   // KryPvfgmres.c:147-167, xx = ||b||^2 here
+        const double b_norm = sqrt(st->xx);
+        st->den_norm = (b_norm > 0.0) ? b_norm : st->r_norm;
+        st->epsilon  = st->tol * st->den_norm;
+        st->absres0 = st->absres = st->r_norm;
+        st->relres  = (b_norm > 0.0) ? st->r_norm / b_norm : st->r_norm;
+        norms[0]    = st->relres;
+        habs[0]     = st->r_norm;
+        if (st->r_norm < st->epsilon || st->r_norm < st->abstol || st->r_norm == 0.0) {
+            st->converged = 1;
+            st->done      = 1;
+            st->silent    = 1;   // "goto FINISHED" / early return: no final line
+        }
+        return;
+    }
     if (st->stop_type == STOP_MOD_REL_RES) {
         st->normu   = fmax(SMALLREAL, sqrt(st->xx));
         st->absres0 = st->r_norm;
@@ -56,6 +74,9 @@ __global__ void k_gm_init(GmState* st, double* norms)
 // rs[0] = r_norm_old = r_norm ; p0 *= 1/r_norm                    (:190-195)
 __global__ void k_gm_cycle_start(GmState* st, double* rs)
 {
+    if (!st->done && st->flexible && st->r_norm == 0.0) {   // KryPvfgmres.c:181-188
+        st->done = st->converged = st->silent = 1;
+    }
     if (st->done) {
         st->skip_inner = 1;
         return;
@@ -122,7 +143,7 @@ __global__ void k_gm_givens(GmState* st, double* hh, double* c, double* s, doubl
     st->iter += 1;
     double t                      = sqrt(st->t2);
     hh[(size_t)i * R + (i - 1)]   = t;
-    const bool do_scale           = st->variable ? (t != 0.0) : (fabs(t) > SMALLREAL);
+    const bool do_scale           = (st->variable || st->flexible) ? (t != 0.0) : (fabs(t) > SMALLREAL);
     st->scale                     = do_scale ? 1.0 / t : 1.0;
     st->skip_scale                = 0;
     for (int j = 1; j < i; ++j) {
@@ -135,7 +156,7 @@ __global__ void k_gm_givens(GmState* st, double* hh, double* c, double* s, doubl
     t                = hi * hi;
     t += hd * hd;
     double gamma = sqrt(t);
-    if (st->variable) {
+    if (st->variable || st->flexible) {
         if (gamma == 0.0) gamma = SMALLREAL;
     } else {
         gamma = fmax(gamma, SMALLREAL);
@@ -146,6 +167,13 @@ __global__ void k_gm_givens(GmState* st, double* hh, double* c, double* s, doubl
     rs[i - 1] = c[i - 1] * rs[i - 1];
     hh[(size_t)(i - 1) * R + (i - 1)] = s[i - 1] * hi + c[i - 1] * hd;
     st->absres = st->r_norm = fabs(rs[i]);
+    if (st->flexible) {   // KryPvfgmres.c:258-273: table relative to ||b||, exit on r_norm <= epsilon
+        st->relres      = (st->den_norm > 0.0) ? st->r_norm / st->den_norm : st->r_norm;
+        norms[st->iter] = st->relres;
+        hfac[st->iter]  = st->absres;
+        if (st->r_norm <= st->epsilon || st->iter >= st->maxit) st->skip_inner = 1;
+        return;
+    }
     st->relres              = st->absres / st->absres0;
     norms[st->iter]         = st->relres;
     hfac[st->iter]          = st->absres;
@@ -194,7 +222,7 @@ k_gm_add(const GmState* st, const double* __restrict__ r, double* __restrict__ x
 __global__ void k_gm_after_update(GmState* st)
 {
     if (st->done) return;
-    st->skip_true = !(st->relres < st->tol);
+    st->skip_true = st->flexible ? !(st->r_norm <= st->epsilon) : !(st->relres < st->tol);
 }
 
 // false-convergence check with the true residual (KryPvgmres.c:295-340)
@@ -204,6 +232,24 @@ __global__ void k_gm_truecheck(GmState* st, double* norms)
     st->skip_true = 1;
     st->r_norm    = sqrt(st->rr);
     st->absres    = st->r_norm;
+    if (st->flexible) {   // KryPvfgmres.c:294-325
+        double relres;
+        if (st->stop_type == STOP_MOD_REL_RES) {
+            st->normu = fmax(SMALLREAL, sqrt(st->xx));
+            relres    = st->r_norm / st->normu;
+        } else {
+            relres = st->r_norm / st->den_norm;
+        }
+        st->relres = st->r_norm / st->den_norm;   // what ITS_FINAL reports (:358)
+        if (relres <= st->tol) {
+            st->converged = 1;
+            st->done      = 1;
+        } else {
+            st->skip_copy = 0;
+            st->i         = 0;
+        }
+        return;
+    }
     if (st->stop_type == STOP_MOD_REL_RES) {
         st->normu  = fmax(SMALLREAL, sqrt(st->xx));
         st->relres = st->absres / st->normu;
@@ -273,9 +319,11 @@ static int ggrid(size_t n)
 }
 
 int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, double abstol,
-                int MaxIt, int restart, int StopType, int PrtLvl, bool variable,
+                int MaxIt, int restart, int StopType, int PrtLvl, int kind,
                 SolveStats* stats)
 {
+    const bool flexible = (kind == GM_FLEXIBLE);
+    const bool variable = (kind == GM_VARIABLE) || flexible;   // both adapt the restart length
     ensure_init();
     Ctx&         c = ctx();
     const size_t n = (size_t)A.n;
@@ -285,7 +333,8 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
              StopType);
     if (restart < 1) fail(ERROR_INPUT_PAR, "GMRES restart must be positive");
     if (PrtLvl > PRINT_NONE)
-        printf(variable ? "\nCalling VGMRes solver (CSR) ...\n" : "\nCalling GMRes solver (CSR) ...\n");
+        printf("\nCalling %s solver (%s) ...\n", flexible ? "VFGMRes" : (variable ? "VGMRes" : "GMRes"),
+               A.format());
 
     const long long launches0   = c.launches;
     const int       restart_max = variable ? restart : (restart < MaxIt ? restart : (MaxIt > 0 ? MaxIt : 1));
@@ -315,14 +364,16 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
     };
 
     try {
-        // basis p[0..R], w, r ; hh (R+1) x R, c, s, rs ; norms + absres history
+        // basis p[0..R], w, r, (flexible: z[0..R-1]) ; hh (R+1) x R, c, s, rs ; norms + absres history
         const size_t nsmall = (size_t)(R + 1) * R + 2 * (size_t)R + (R + 1) + 2 * (size_t)hcap;
-        work       = dalloc<double>((size_t)(R + 3) * ldp + nsmall);
-        if (p2p_active()) p2p_register(work, sizeof(double) * ((size_t)(R + 3) * ldp + nsmall));
+        const size_t nvec   = (size_t)(R + 3) + (flexible ? (size_t)R : 0);
+        work       = dalloc<double>(nvec * ldp + nsmall);
+        if (p2p_active()) p2p_register(work, sizeof(double) * (nvec * ldp + nsmall));
         double* P  = work;
         double* w  = P + (size_t)(R + 1) * ldp;
         double* r  = w + ldp;
-        double* hh = r + ldp;
+        double* Z  = r + ldp;
+        double* hh = Z + (flexible ? (size_t)R * ldp : 0);
         double* cc = hh + (size_t)(R + 1) * R;
         double* ss = cc + R;
         double* rs = ss + R;
@@ -337,7 +388,7 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
         GmState h0;
         memset(&h0, 0, sizeof(h0));
         h0.tol = tol, h0.abstol = abstol, h0.maxit = MaxIt, h0.stop_type = StopType;
-        h0.variable = variable ? 1 : 0, h0.R = R, h0.cr = 1.0;
+        h0.variable = (variable && !flexible) ? 1 : 0, h0.flexible = flexible ? 1 : 0, h0.R = R, h0.cr = 1.0;
         h0.skip_inner = h0.skip_scale = h0.skip_true = h0.skip_copy = 1;
         h0.absres0 = h0.absres = h0.relres = h0.normu = BIGREAL;
         FC_CUDA(cudaMemcpyAsync(st, &h0, sizeof(h0), cudaMemcpyHostToDevice, c.stream));
@@ -352,13 +403,13 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
             red.global = true;
             red.nrm2_out = &st->rr;
             A.apply(CSR_RESID, 1.0, x, b, pvec(0), red, nullptr);
-            if (StopType == STOP_MOD_REL_RES) {
+            if (flexible || StopType == STOP_MOD_REL_RES) {
                 Reduce rx;
-            rx.global = true;
+                rx.global   = true;
                 rx.nrm2_out = &st->xx;
-                vec_reduce(x, n, rx, nullptr);
+                vec_reduce(flexible ? b : x, n, rx, nullptr);   // flexible: ||b|| (KryPvfgmres.c:150)
             }
-            FC_LAUNCH(k_gm_init, 1, 1, 0, st, norms);
+            FC_LAUNCH(k_gm_init, 1, 1, 0, st, norms, habs);
             FC_LAUNCH(k_gm_cycle_end, 1, 1, 0, st, pin_d);
             FC_CUDA(cudaMemcpyAsync(pin_h, pin_d, sizeof(GmPinned), cudaMemcpyDeviceToHost, c.stream));
             FC_CUDA(cudaStreamSynchronize(c.stream));
@@ -366,8 +417,9 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
 
         auto inner_step = [&](int i) {
             const int* gate = &st->skip_inner;
-            pc.apply(pvec(i - 1), r, Reduce(), gate);
-            A.apply(CSR_MXV, 1.0, r, nullptr, pvec(i), Reduce(), gate);
+            double* zi = flexible ? Z + (size_t)(i - 1) * ldp : r;   // flexible keeps z_{i-1} (:226-231)
+            pc.apply(pvec(i - 1), zi, Reduce(), gate);
+            A.apply(CSR_MXV, 1.0, zi, nullptr, pvec(i), Reduce(), gate);
             for (int j = 0; j <= i; ++j)
             {
                 FC_LAUNCH(k_gm_mgs, g, 256, 0, st, hh, j, i, j > 0 ? pvec(j - 1) : nullptr,
@@ -384,8 +436,12 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
         auto cycle_end = [&]() {
             const int* done = &st->done;
             FC_LAUNCH(k_gm_backsolve, 1, 1, 0, st, hh, rs);
-            FC_LAUNCH(k_gm_form_w, g, 256, 0, st, rs, P, ldp, w, n);
-            pc.apply(w, r, Reduce(), done);
+            if (flexible) {   // x += sum_j rs_j z_j (KryPvfgmres.c:286-291), no preconditioner call
+                FC_LAUNCH(k_gm_form_w, g, 256, 0, st, rs, Z, ldp, r, n);
+            } else {
+                FC_LAUNCH(k_gm_form_w, g, 256, 0, st, rs, P, ldp, w, n);
+                pc.apply(w, r, Reduce(), done);
+            }
             FC_LAUNCH(k_gm_add, g, 256, 0, st, r, x, n);
             FC_LAUNCH(k_gm_after_update, 1, 1, 0, st);
             Reduce red;
@@ -449,7 +505,7 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
                 stats->hist_factor.clear();
             }
         }
-        if (PrtLvl > PRINT_NONE) print_final(hs.iter, MaxIt, hs.relres);
+        if (PrtLvl > PRINT_NONE && !hs.silent) print_final(hs.iter, MaxIt, hs.relres);
         float ms = 0.f;
         FC_CUDA(cudaEventElapsedTime(&ms, t0, t1));
         if (stats) {

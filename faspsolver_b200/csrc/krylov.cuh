@@ -11,6 +11,7 @@ struct LinOp {
     virtual ~LinOp() {}
     virtual const void* key() const { return this; }   // identity of the resident operator
     virtual size_t      vec_capacity() const { return (size_t)n; }   // entries a gathered vector must hold
+    virtual const char* format() const { return "CSR"; }             // name in the "Calling ... solver" line
     // mode: CSR_MXV / CSR_AXPY / CSR_RESID semantics
     virtual void apply(int mode, double alpha, const double* x, const double* b, double* y,
                        const Reduce& red, const int* done, bool conditional = false) = 0;
@@ -43,6 +44,7 @@ struct BsrOp : LinOp {
     const DevBSR* A;
     explicit BsrOp(const DevBSR* a) : A(a) { n = a->ROW * a->nb; }
     const void* key() const override { return A; }
+    const char* format() const override { return "BSR"; }
     void apply(int mode, double alpha, const double* x, const double* b, double* y,
                const Reduce& red, const int* done, bool conditional = false) override
     {
@@ -135,9 +137,11 @@ struct PcgCache {
 // All vectors are device pointers. Returns FASP status (>=0 iterations, <0 ERROR_*).
 int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double abstol,
               int MaxIt, int StopType, int PrtLvl, SolveStats* stats, PcgCache* cache = nullptr);
-// restart > 0; variable == true -> Baker/Jessup/Kolev restart adaptation (KryPvgmres.c)
+// restart > 0; kind: fixed restart (KryPgmres.c), Baker/Jessup/Kolev restart adaptation
+// (KryPvgmres.c), or the flexible variant that stores the preconditioned basis (KryPvfgmres.c)
+enum { GM_FIXED = 0, GM_VARIABLE = 1, GM_FLEXIBLE = 2 };
 int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, double abstol,
-                int MaxIt, int restart, int StopType, int PrtLvl, bool variable,
+                int MaxIt, int restart, int StopType, int PrtLvl, int kind,
                 SolveStats* stats);
 
 // FASP's iteration table / final line (AuxMessage.c:41-76, KryUtil.inl:93-103)

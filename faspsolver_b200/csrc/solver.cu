@@ -122,13 +122,16 @@ static int run_krylov(fasp_cuda_solver_s* s, LinOp& op, Prec& pc, const double* 
                              it->print_level, &s->stats, &s->pcg_cache);
         case SOLVER_GMRES:
             return gmres_solve(op, b_dev, x_dev, pc, it->tol, it->abstol, it->maxit, it->restart,
-                               it->stop_type, it->print_level, false, &s->stats);
+                               it->stop_type, it->print_level, GM_FIXED, &s->stats);
         case SOLVER_VGMRES:
             return gmres_solve(op, b_dev, x_dev, pc, it->tol, it->abstol, it->maxit, it->restart,
-                               it->stop_type, it->print_level, true, &s->stats);
+                               it->stop_type, it->print_level, GM_VARIABLE, &s->stats);
+        case SOLVER_VFGMRES:
+            return gmres_solve(op, b_dev, x_dev, pc, it->tol, it->abstol, it->maxit, it->restart,
+                               it->stop_type, it->print_level, GM_FLEXIBLE, &s->stats);
         default:
             fail(ERROR_SOLVER_TYPE,
-                 "itsolver_type %d not on the device path (supported: CG 1, GMRES 4, VGMRES 5)",
+                 "itsolver_type %d not on the device path (supported: CG 1, GMRES 4, VGMRES 5, VFGMRES 6)",
                  (int)it->itsolver_type);
     }
 }

@@ -225,6 +225,12 @@ INT fasp_cuda_solver_dcsr_pgmres(dCSRmat* A, dvector* b, dvector* x, precond* pc
                                  const REAL tol, const REAL abstol, const INT MaxIt,
                                  const SHORT restart, const SHORT StopType,
                                  const SHORT PrtLvl);
+/* replaces fasp_solver_dcsr_pvfgmres KryPvfgmres.c:67 (flexible: stores z_j = B p_j, so the
+ * preconditioner may change between iterations; stops on ||r|| <= tol * ||b||)            */
+INT fasp_cuda_solver_dcsr_pvfgmres(dCSRmat* A, dvector* b, dvector* x, precond* pc,
+                                   const REAL tol, const REAL abstol, const INT MaxIt,
+                                   const SHORT restart, const SHORT StopType,
+                                   const SHORT PrtLvl);
 /* replaces fasp_solver_dbsr_pcg      KryPcg.c:386 */
 INT fasp_cuda_solver_dbsr_pcg(dBSRmat* A, dvector* b, dvector* u, precond* pc, const REAL tol,
                               const REAL abstol, const INT MaxIt, const SHORT StopType,
@@ -239,6 +245,11 @@ INT fasp_cuda_solver_dbsr_pgmres(dBSRmat* A, dvector* b, dvector* x, precond* pc
                                  const REAL tol, const REAL abstol, const INT MaxIt,
                                  const SHORT restart, const SHORT StopType,
                                  const SHORT PrtLvl);
+/* replaces fasp_solver_dbsr_pvfgmres KryPvfgmres.c:386 */
+INT fasp_cuda_solver_dbsr_pvfgmres(dBSRmat* A, dvector* b, dvector* x, precond* pc,
+                                   const REAL tol, const REAL abstol, const INT MaxIt,
+                                   const SHORT restart, const SHORT StopType,
+                                   const SHORT PrtLvl);
 
 /* ------------------------------------------------------------------------------------ */
 /* Level-5: drivers                                                                       */

@@ -533,3 +533,107 @@ FINISHED:
     free(p), free(hh), free(r), free(w), free(rs), free(c), free(s);
     return iter >= MaxIt ? ERROR_SOLVER_MAXIT : iter;
 }
+
+/* ---- flexible variable-restart GMRES: KryPvfgmres.c:67-358. Differences from oracle_gmres:
+ *      z_j = B p_j is kept per step (:226-231) and the update is x += sum rs_j z_j (:286-291);
+ *      the inner exit is r_norm <= tol * den_norm with den_norm = ||b|| (or ||r0|| if b = 0)
+ *      (:153-158, :273); the true-residual recheck uses r_norm / den_norm <= tol (:294-317).
+ *      relres_out receives r_norm / den_norm as printed by ITS_FINAL (:358). ---- */
+int oracle_fgmres(int n, const int* ia, const int* ja, const double* val, const double* b, double* x, omg* pc,
+                  double tol, double abstol, int MaxIt, int restart, double* relres_out)
+{
+    const double cr_max = 0.99, cr_min = 0.174;
+    int    iter = 0, i, j, k, d = 3, restart_max = restart, restart_min = 3, Restart = restart;
+    const int R1 = restart + 1;
+    double r_norm, b_norm, den_norm, epsilon, gamma, t, cr = 1.0, r_norm_old = 0.0;
+    double *r = calloc(n, 8), *rs = calloc(R1 + 1, 8), *c = calloc(R1, 8), *s = calloc(R1, 8);
+    double** p  = malloc(R1 * sizeof(double*));
+    double** z  = malloc(R1 * sizeof(double*));
+    double** hh = malloc(R1 * sizeof(double*));
+    for (i = 0; i < R1; ++i) p[i] = calloc(n, 8), z[i] = calloc(n, 8), hh[i] = calloc(R1, 8);
+    memcpy(p[0], b, n * 8);
+    oracle_dcsr_aAxpy(-1.0, n, ia, ja, val, x, p[0]);
+    b_norm   = o_norm2(n, b);
+    r_norm   = o_norm2(n, p[0]);
+    den_norm = b_norm > 0.0 ? b_norm : r_norm;
+    epsilon  = tol * den_norm;
+    if (r_norm < epsilon || r_norm < abstol) goto FINISHED;
+    while (iter < MaxIt) {
+        rs[0] = r_norm_old = r_norm;
+        if (r_norm == 0.0) break;
+        if (cr > cr_max || iter == 0) Restart = restart_max;
+        else if (cr < cr_min) { }
+        else if (Restart - d > restart_min) Restart -= d;
+        else Restart = restart_max;
+        t = 1.0 / r_norm;
+        for (k = 0; k < n; ++k) p[0][k] *= t;
+        i = 0;
+        while (i < Restart && iter < MaxIt) {
+            i++, iter++;
+            if (pc) oracle_precond_amg(pc, p[i - 1], z[i - 1], 1);
+            else memcpy(z[i - 1], p[i - 1], n * 8);
+            oracle_dcsr_mxv(n, ia, ja, val, z[i - 1], p[i]);
+            for (j = 0; j < i; j++) {
+                hh[j][i - 1] = o_dot(n, p[j], p[i]);
+                o_axpy(n, -hh[j][i - 1], p[j], p[i]);
+            }
+            t = o_norm2(n, p[i]);
+            hh[i][i - 1] = t;
+            if (t != 0.0) {
+                t = 1.0 / t;
+                for (k = 0; k < n; ++k) p[i][k] *= t;
+            }
+            for (j = 1; j < i; ++j) {
+                t = hh[j - 1][i - 1];
+                hh[j - 1][i - 1] = s[j - 1] * hh[j][i - 1] + c[j - 1] * t;
+                hh[j][i - 1]     = -s[j - 1] * t + c[j - 1] * hh[j][i - 1];
+            }
+            t = hh[i][i - 1] * hh[i][i - 1];
+            t += hh[i - 1][i - 1] * hh[i - 1][i - 1];
+            gamma = sqrt(t);
+            if (gamma == 0.0) gamma = SMALLREAL;
+            c[i - 1] = hh[i - 1][i - 1] / gamma;
+            s[i - 1] = hh[i][i - 1] / gamma;
+            rs[i]     = -s[i - 1] * rs[i - 1];
+            rs[i - 1] = c[i - 1] * rs[i - 1];
+            hh[i - 1][i - 1] = s[i - 1] * hh[i][i - 1] + c[i - 1] * hh[i - 1][i - 1];
+            r_norm = fabs(rs[i]);
+            if (r_norm <= epsilon) break;
+        }
+        rs[i - 1] = rs[i - 1] / hh[i - 1][i - 1];
+        for (k = i - 2; k >= 0; k--) {
+            t = 0.0;
+            for (j = k + 1; j < i; j++) t -= hh[k][j] * rs[j];
+            t += rs[k];
+            rs[k] = t / hh[k][k];
+        }
+        memcpy(r, z[i - 1], n * 8);
+        if (rs[i - 1] != 1.0) for (k = 0; k < n; ++k) r[k] *= rs[i - 1];
+        for (j = i - 2; j >= 0; j--) o_axpy(n, rs[j], z[j], r);
+        o_axpy(n, 1.0, r, x);
+        if (r_norm <= epsilon) {
+            memcpy(r, b, n * 8);
+            oracle_dcsr_aAxpy(-1.0, n, ia, ja, val, x, r);
+            r_norm = o_norm2(n, r);
+            if (r_norm / den_norm <= tol) break;
+            memcpy(p[0], r, n * 8);
+            i = 0;
+        }
+        for (j = i; j > 0; j--) {
+            rs[j - 1] = -s[j - 1] * rs[j];
+            rs[j]     = c[j - 1] * rs[j];
+        }
+        if (i) o_axpy(n, rs[i] - 1.0, p[i], p[i]);
+        for (j = i - 1; j > 0; j--) o_axpy(n, rs[j], p[j], p[i]);
+        if (i) {
+            o_axpy(n, rs[0] - 1.0, p[0], p[0]);
+            o_axpy(n, 1.0, p[i], p[0]);
+        }
+        cr = r_norm / r_norm_old;
+    }
+FINISHED:
+    if (relres_out) *relres_out = den_norm > 0.0 ? r_norm / den_norm : 0.0;
+    for (i = 0; i < R1; ++i) free(p[i]), free(z[i]), free(hh[i]);
+    free(p), free(z), free(hh), free(r), free(rs), free(c), free(s);
+    return iter >= MaxIt ? ERROR_SOLVER_MAXIT : iter;
+}

@@ -47,6 +47,8 @@ class Oracle:
         L.oracle_pcg.restype = I
         L.oracle_gmres.argtypes = [I, PI, PI, PD, PD, PD, VP, D, D, I, I, I, PD]
         L.oracle_gmres.restype = I
+        L.oracle_fgmres.argtypes = [I, PI, PI, PD, PD, PD, VP, D, D, I, I, PD]
+        L.oracle_fgmres.restype = I
         for f in ("oracle_dcsr_mxv", "oracle_dcsr_aAxpy", "oracle_smoother_jacobi", "oracle_smoother_l1diag",
                   "oracle_smoother_poly", "oracle_dbsr_mxv", "oracle_dbsr_aAxpy", "oracle_dbsr_jacobi1",
                   "oracle_mg_set_level", "oracle_mg_free", "oracle_precond_amg", "oracle_mg_cycle_on"):
@@ -114,6 +116,13 @@ class OracleMG:
         rel = C.c_double(0)
         st = self.orc.L.oracle_gmres(A.shape[0], _pi(A.ia), _pi(A.ja), _pd(A.val), _pd(np.ascontiguousarray(b)), _pd(x),
                                      self.h if precond else None, tol, 1e-18, maxit, restart, int(variable), C.byref(rel))
+        return st, x, rel.value
+
+    def fgmres(self, A, b, tol=1e-8, maxit=500, restart=30, precond=True):
+        x = np.zeros_like(b)
+        rel = C.c_double(0)
+        st = self.orc.L.oracle_fgmres(A.shape[0], _pi(A.ia), _pi(A.ja), _pd(A.val), _pd(np.ascontiguousarray(b)), _pd(x),
+                                      self.h if precond else None, tol, 1e-18, maxit, restart, C.byref(rel))
         return st, x, rel.value
 
     def close(self):

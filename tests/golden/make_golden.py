@@ -50,6 +50,9 @@ def main():
         "FE_amg_pcg_default_tol1e-10": {"iters": 6, "relres": 2.728796e-11, "line": 577},
         "FD_amg_pcg_default_tol1e-10": {"iters": 1, "relres": 4.938174e-15, "line": 255},
         "FE_amg_solver_L1DIAG_tol1e-10": {"iters": 19, "relres": 8.612004e-11, "line": 412},
+        # unpreconditioned variable-restart GMRES and its flexible twin, tol 1e-12, restart 25
+        "FE_vgmres_unprec_tol1e-12": {"iters": 493, "relres": 7.667271e-13, "line": 500},
+        "FE_vfgmres_unprec_tol1e-12": {"iters": 493, "relres": 7.667271e-13, "line": 514},
     }, "recipes": []}
 
     def run(name, A, b, it_kw, amg_kw):
@@ -79,6 +82,8 @@ def main():
                               dict(smoother=T.SMOOTHER_L1DIAG))
     xs["FE_x_vgmres_poly3"] = run("FE_vgmres30_poly3", FE, bFE, dict(itsolver_type=T.SOLVER_VGMRES, restart=30),
                                   dict(smoother=T.SMOOTHER_POLY, polynomial_degree=3))
+    xs["FE_x_vfgmres_l1"] = run("FE_vfgmres30_l1", FE, bFE, dict(itsolver_type=T.SOLVER_VFGMRES, restart=30),
+                                dict(smoother=T.SMOOTHER_L1DIAG))
     run("FE_pcg_l1_W", FE, bFE, dict(itsolver_type=T.SOLVER_CG),
         dict(smoother=T.SMOOTHER_L1DIAG, cycle_type=T.W_CYCLE))
     run("FE_pcg_jacobi067_sa", FE, bFE, dict(itsolver_type=T.SOLVER_CG),

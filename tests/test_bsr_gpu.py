@@ -110,3 +110,25 @@ def test_bsr_krylov_no_precond(gpu, ref, data):
     if st > 0:
         assert abs(st - st_ref) <= 2
         assert np.linalg.norm(vx.a - vxr.a) / np.linalg.norm(vxr.a) < 1e-5
+
+
+def test_bsr_flexible_gmres(gpu, ref, data):
+    """fasp_solver_dbsr_pvfgmres (KryPvfgmres.c:386): pc == NULL on SPE01 and, through the driver, the
+    UA-AMG recipe FASP's own BSR Fortran wrapper selects (SolWrapper.c:425)."""
+    A, b = data["SPE"], data["SPE_b"]
+    vb, vx, vxr = T.Vec(b), T.Vec(np.zeros_like(b)), T.Vec(np.zeros_like(b))
+    st = gpu.fasp_cuda_solver_dbsr_pvfgmres(A.ptr(), vb.ptr(), vx.ptr(), None, 1e-6, 1e-18, 500, 30, 1, 0)
+    st_ref = ref.L.fasp_solver_dbsr_pvfgmres(A.ptr(), vb.ptr(), vxr.ptr(), None, 1e-6, 1e-18, 500, 30, 1, 0)
+    assert (st > 0) == (st_ref > 0), (st, st_ref)
+    if st > 0:
+        assert abs(st - st_ref) <= 2
+        assert np.linalg.norm(vx.a - vxr.a) / np.linalg.norm(vxr.a) < 1e-5
+    A, b = PB.blockoil7(12)
+    it = ref.its_param(itsolver_type=T.SOLVER_VFGMRES, restart=30, tol=1e-8, maxit=500, print_level=0)
+    vb, vx, vxr = T.Vec(b), T.Vec(np.zeros_like(b)), T.Vec(np.zeros_like(b))
+    st_ref = ref.L.fasp_solver_dbsr_krylov_amg(A.ptr(), vb.ptr(), vxr.ptr(), C.byref(it), C.byref(_bsr_amg(ref)))
+    st = gpu.fasp_cuda_solver_dbsr_krylov_amg(A.ptr(), vb.ptr(), vx.ptr(), C.byref(it), C.byref(_bsr_amg(ref)))
+    assert st > 0, (st, gpu.fasp_cuda_last_error())
+    assert st <= st_ref + 2, (st, st_ref)
+    assert np.linalg.norm(b - A.to_scipy() @ vx.a) / np.linalg.norm(b) <= 1e-8 * 1.001
+    assert np.linalg.norm(vx.a - vxr.a) / np.linalg.norm(vxr.a) < 1e-6

@@ -88,6 +88,9 @@ SOLVE_CASES = [
     ("FE", dict(itsolver_type=T.SOLVER_VGMRES, restart=30), dict(smoother=T.SMOOTHER_POLY, polynomial_degree=3)),
     ("FE", dict(itsolver_type=T.SOLVER_GMRES, restart=3), dict(smoother=T.SMOOTHER_JACOBI, relaxation=0.67)),
     ("FE", dict(itsolver_type=T.SOLVER_VGMRES, restart=4), dict(smoother=T.SMOOTHER_JACOBI, relaxation=0.67)),
+    ("FE", dict(itsolver_type=T.SOLVER_VFGMRES, restart=30), dict(smoother=T.SMOOTHER_L1DIAG)),
+    ("FE", dict(itsolver_type=T.SOLVER_VFGMRES, restart=4), dict(smoother=T.SMOOTHER_JACOBI, relaxation=0.67)),
+    ("cd7", dict(itsolver_type=T.SOLVER_VFGMRES, restart=30), dict(smoother=T.SMOOTHER_POLY, polynomial_degree=3)),
     ("FE", dict(itsolver_type=T.SOLVER_CG), dict(smoother=T.SMOOTHER_JACOBI, relaxation=0.67, AMG_type=T.SA_AMG)),
     ("FE", dict(itsolver_type=T.SOLVER_CG), dict(smoother=T.SMOOTHER_JACOBI, relaxation=0.67, AMG_type=T.UA_AMG)),
     ("p7", dict(itsolver_type=T.SOLVER_CG), dict(smoother=T.SMOOTHER_L1DIAG)),
@@ -125,7 +128,7 @@ def test_golden_iteration_counts(gpu, ref, data, golden_answers):
     """The committed oracle answers (tests/golden/oracle_answers.json) for the recipes above."""
     by_name = {r["name"]: r for r in golden_answers["recipes"]}
     for name, prob in (("FE_pcg_jacobi067", "FE"), ("FE_pcg_l1", "FE"), ("FE_pcg_poly3", "FE"),
-                       ("FE_gmres30_l1", "FE"), ("FD_pcg_l1_cdof20", "FD")):
+                       ("FE_gmres30_l1", "FE"), ("FE_vfgmres30_l1", "FE"), ("FD_pcg_l1_cdof20", "FD")):
         rec = by_name[name]
         A, b = data[prob], data[prob + "_b"]
         it = ref.its_param(tol=1e-8, maxit=500, print_level=0, **rec["it"])

@@ -72,7 +72,7 @@ ORACLE_SOLVES = [
     ("FE_pcg_jacobi067", "pcg", {}), ("FE_pcg_l1", "pcg", {}), ("FE_pcg_poly3", "pcg", {}),
     ("FE_pcg_l1_W", "pcg", {}), ("FE_gmres30_l1", "gmres", dict(variable=False)),
     ("FE_vgmres30_poly3", "gmres", dict(variable=True)), ("FD_pcg_jacobi067_cdof20", "pcg", {}),
-    ("FD_pcg_l1_cdof20", "pcg", {}),
+    ("FD_pcg_l1_cdof20", "pcg", {}), ("FE_vfgmres30_l1", "fgmres", {}),
 ]
 
 
@@ -94,6 +94,8 @@ def test_oracle_solves_reproduce_reference_answers(orc, ref, data, golden_answer
                   postsmooth=amg.postsmooth_iter, ndeg=amg.polynomial_degree, relax=amg.relaxation, tol=1e-6)
     if method == "pcg":
         st, x, rel = mg.pcg(A, b, tol=1e-8)
+    elif method == "fgmres":
+        st, x, rel = mg.fgmres(A, b, tol=1e-8, restart=rec["it"]["restart"])
     else:
         st, x, rel = mg.gmres(A, b, tol=1e-8, restart=rec["it"]["restart"], **kw)
     mg.close()
@@ -143,3 +145,22 @@ def test_reference_reproduces_reg_gcc_golden_lines(ref, data, golden_answers):
     assert st == g["FE_amg_solver_L1DIAG_tol1e-10"]["iters"]
     rel = np.linalg.norm(b - A.to_scipy() @ vx.a) / np.linalg.norm(b)
     assert abs(rel - g["FE_amg_solver_L1DIAG_tol1e-10"]["relres"]) / rel < 1e-5
+
+
+def test_oracle_flexible_gmres_reproduces_reg_gcc_line(orc, ref, data, golden_answers):
+    """Unpreconditioned VFGMRES on the FE problem (test/main/regression.c:492-505, tol 1e-12, default
+    restart 25): reg.gcc pins 493 iterations / 7.667271e-13. The restatement and the compiled
+    reference both reproduce it, bit-identical to each other."""
+    from oracle.port import OracleMG
+    g = golden_answers["reg_gcc"]["FE_vfgmres_unprec_tol1e-12"]
+    A, b = data["FE"], data["FE_b"]
+    n = A.shape[0]
+    mg = OracleMG.__new__(OracleMG)   # no hierarchy needed for pc == NULL
+    mg.orc, mg.h = orc, None
+    st, x, rel = mg.fgmres(A, b, tol=1e-12, maxit=5000, restart=25, precond=False)
+    vb, vx = T.Vec(b), T.Vec(np.zeros(n))
+    st_ref = ref.L.fasp_solver_dcsr_pvfgmres(A.ptr(), vb.ptr(), vx.ptr(), None, 1e-12, 1e-20, 5000, 25, 1, 0)
+    assert st == st_ref == g["iters"]
+    assert float("%.6e" % rel) == g["relres"]
+    assert np.array_equal(x, vx.a)
+    assert np.abs(x - data["FE_sol"]).max() < 1e-4
