@@ -99,6 +99,8 @@ def lib():
         "fasp_cuda_solver_dbsr_pcg": (INT, [P(dBSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT]),
         "fasp_cuda_solver_dbsr_pvgmres": (INT, [P(dBSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT, SHORT]),
         "fasp_cuda_solver_dbsr_pgmres": (INT, [P(dBSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT, SHORT]),
+        "fasp_cuda_host_pin": (INT, [vp, C.c_size_t]),
+        "fasp_cuda_host_unpin": (INT, [vp]),
         "fasp_cuda_solver_dcsr_itsolver": (INT, [P(dCSRmat), P(dvector), P(dvector), P(precond), P(ITS_param)]),
         "fasp_cuda_solver_dbsr_itsolver": (INT, [P(dBSRmat), P(dvector), P(dvector), P(precond), P(ITS_param)]),
         "fasp_cuda_solver_dcsr_krylov_amg": (INT, [P(dCSRmat), P(dvector), P(dvector), P(ITS_param), P(AMG_param)]),
@@ -153,6 +155,16 @@ def check(status: int) -> int:
     if status < 0:
         raise FaspCudaError(status, last_error())
     return status
+
+
+def pin_host(a: np.ndarray) -> None:
+    """Page-lock a long-lived application array (b / x of repeated solves): the host-pointer solve
+    then copies it by DMA. Call unpin_host before the array is released."""
+    check(lib().fasp_cuda_host_pin(a.ctypes.data, a.nbytes))
+
+
+def unpin_host(a: np.ndarray) -> None:
+    check(lib().fasp_cuda_host_unpin(a.ctypes.data))
 
 
 # ---------------------------------------------------------------------------------------

@@ -164,6 +164,9 @@ static int* option_slot(const char* key)
     if (!strcmp(key, "sort_rows")) return &o.sort_rows;
     if (!strcmp(key, "host_register")) return &o.host_register;
     if (!strcmp(key, "rowwise_max")) return &o.rowwise_max;
+    if (!strcmp(key, "l2_hint")) return &o.l2_hint;
+    if (!strcmp(key, "p2p_fused")) return &o.p2p_fused;
+    if (!strcmp(key, "wide_threads")) return &o.wide_threads;
     if (!strcmp(key, "vec_lpr")) return &o.vec_lpr;
     if (!strcmp(key, "gs_multicolor")) return &o.gs_multicolor;
     return nullptr;
@@ -839,6 +842,36 @@ INT fasp_cuda_solver_dcsr_itsolver(dCSRmat* A, dvector* b, dvector* x, precond* 
 // ------------------------------------------------------------------------------------
 // drivers
 // ------------------------------------------------------------------------------------
+INT fasp_cuda_host_pin(void* p, size_t bytes)
+{
+    API_TRY
+    ensure_init();
+    if (!p || bytes == 0) fail(ERROR_INPUT_PAR, "fasp_cuda_host_pin: null buffer");
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return FASP_SUCCESS;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(ERROR_ALLOC_MEM, "cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+INT fasp_cuda_host_unpin(void* p)
+{
+    API_TRY
+    if (!p) return FASP_SUCCESS;
+    FC_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (cudaHostUnregister(p) != cudaSuccess) {
+        cudaGetLastError();
+        fail(ERROR_INPUT_PAR, "fasp_cuda_host_unpin: buffer was not pinned");
+    }
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+
 fasp_cuda_solver* fasp_cuda_krylov_amg_create(AMG_data* mgl, AMG_param* amgparam)
 {
     API_TRY

@@ -158,13 +158,21 @@ int solver_solve_host(fasp_cuda_solver_s* s, const double* b, double* x, ITS_par
     Ctx&         c  = ctx();
     const size_t n  = s->n;
     const auto   w0 = std::chrono::steady_clock::now();
-    // Caller buffers are page-locked in place the first time they are seen (cudaHostRegister is
-    // slow, so the registration is remembered: applications solve many right-hand sides with the
-    // same arrays); the copies are then plain DMA transfers. A buffer that cannot be registered
-    // goes through the pinned staging area instead.
+    // A caller buffer that is already page-locked (fasp_cuda_host_pin / cudaHostRegister /
+    // cudaMallocHost: the application solves many right-hand sides with the same arrays) is copied
+    // by plain DMA. Anything else goes through the library's pinned staging area (threaded memcpy
+    // overlapping the DMA). host_register=2 makes the library page-lock unknown buffers itself and
+    // REMEMBER them: only for callers that promise not to free or remap those arrays while the
+    // solver lives (a stale registration would DMA into pages the process no longer sees).
     const size_t bytes = sizeof(double) * n;
     auto pinned = [&](const void* p) -> bool {
-        if (!ctx().opt.host_register) return false;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) == cudaSuccess) {
+            if (at.type == cudaMemoryTypeHost) return true;
+        } else {
+            cudaGetLastError();
+        }
+        if (ctx().opt.host_register < 2) return false;
         for (auto& r : s->hostreg)
             if (r.p == p && r.bytes >= bytes) return true;
         if (s->hostreg.size() >= 8) {

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "reduce.cuh"
 #include "pipe.cuh"
+#include "p2p.cuh"
 #include <algorithm>
 #include <thread>
 
@@ -41,6 +42,7 @@ struct CsrView {
     const double* dinv;
     int           cap;
     int           rowwise_max;
+    int           l2hint;   // bit 0: matrix stream evict_first, bit 1: gathered vector evict_last
 };
 
 __device__ __forceinline__ int ld_stream_i32(const int* p)
@@ -165,6 +167,10 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
     auto st_ia  = [&](int s) { return st_ja(s) + cap + 8; };
     const int2* __restrict__ desc = A.blkdesc;   // desc[b] = {first row, ia[first row]}
     const double* __restrict__ x  = a.x;
+    const bool               hx    = (A.l2hint & 2) != 0;
+    const unsigned long long pol_s = l2_policy((A.l2hint & 1) ? 1 : 0);
+    const unsigned long long pol_x = l2_policy(hx ? 2 : 0);
+    auto gx = [&](int col) { return hx ? ld_f64_hint(x + col, pol_x) : __ldg(x + col); };
 
     // thread 0 is the producer: one mbarrier arrival (+ the bulk-copy byte count) per stage use
     auto issue = [&](int blk, int s) {
@@ -177,9 +183,15 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
             const int          r0a = m.r0 & ~3;
             const unsigned int nra = (unsigned int)(((m.r0 + m.nrows + 1 + 3) & ~3) - r0a);
             mbar_expect_tx(&s_bar[s], na * 4u + (PATTERN ? 0u : na * 8u) + nra * 4u);
-            if (na) bulk_g2s(st_ja(s), A.ja + k0a, na * 4u, &s_bar[s]);
-            if (!PATTERN && na) bulk_g2s(st_val(s), A.val + k0a, na * 8u, &s_bar[s]);
-            bulk_g2s(st_ia(s), A.ia + r0a, nra * 4u, &s_bar[s]);
+            if (A.l2hint & 1) {
+                if (na) bulk_g2s_hint(st_ja(s), A.ja + k0a, na * 4u, &s_bar[s], pol_s);
+                if (!PATTERN && na) bulk_g2s_hint(st_val(s), A.val + k0a, na * 8u, &s_bar[s], pol_s);
+                bulk_g2s_hint(st_ia(s), A.ia + r0a, nra * 4u, &s_bar[s], pol_s);
+            } else {
+                if (na) bulk_g2s(st_ja(s), A.ja + k0a, na * 4u, &s_bar[s]);
+                if (!PATTERN && na) bulk_g2s(st_val(s), A.val + k0a, na * 8u, &s_bar[s]);
+                bulk_g2s(st_ia(s), A.ia + r0a, nra * 4u, &s_bar[s]);
+            }
         } else {
             mbar_expect_tx(&s_bar[s], 0u);   // long row: handled from global memory
         }
@@ -195,6 +207,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
         }
     }
     __syncthreads();
+    bool halo_pending = a.hw.mask != 0;   // multi-GPU: wait for the peers' ghost entries lazily
 
     double     red_dot = 0.0, red_n2 = 0.0;
     const bool want_dot = a.red.dot_out != nullptr;
@@ -205,6 +218,11 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
         mbar_wait(&s_bar[s], (unsigned int)ph);
         const PipeMeta m = s_meta[s];
         const int r0 = m.r0, nrows = m.nrows, k0 = m.k0, n = m.n;
+        if (halo_pending && a.hw.touches(r0, r0 + nrows)) {   // first block of this CTA that reads ghosts
+            if (tid == 0) p2p_halo_wait(a.hw);
+            __syncthreads();
+            halo_pending = false;
+        }
         if (n <= cap) {
             double*    sp  = st_val(s) + (k0 & 3);
             const int* sj  = st_ja(s) + (k0 & 3);
@@ -230,7 +248,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
 #pragma unroll
                         for (int u = 0; u < U; ++u) col[u] = (kk + u < kb) ? sj[kk + u] : -1;
 #pragma unroll
-                        for (int u = 0; u < U; ++u) xv[u] = (col[u] >= 0) ? __ldg(x + col[u]) : 0.0;
+                        for (int u = 0; u < U; ++u) xv[u] = (col[u] >= 0) ? gx(col[u]) : 0.0;
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
                             const int k = kk + u;
@@ -256,7 +274,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
                         col[e]      = (k < n) ? sj[k] : -1;
                     }
 #pragma unroll
-                    for (int e = 0; e < EPT; ++e) xv[e] = (col[e] >= 0) ? __ldg(x + col[e]) : 0.0;
+                    for (int e = 0; e < EPT; ++e) xv[e] = (col[e] >= 0) ? gx(col[e]) : 0.0;
 #pragma unroll
                     for (int e = 0; e < EPT; ++e) {
                         const int k = base + tid + e * T;
@@ -354,6 +372,13 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const int nrows, double* par
                   unsigned int* ticket)
 {
     if (a.done != nullptr && *a.done != 0) return;
+    if (a.hw.mask) {
+        const long long f = (long long)blockIdx.x * (TPB / LPR);
+        if (a.hw.touches((int)f, (int)(f + TPB / LPR))) {
+            if (threadIdx.x == 0) p2p_halo_wait(a.hw);
+            __syncthreads();
+        }
+    }
     const long long gt   = (long long)blockIdx.x * TPB + threadIdx.x;
     const int       lane = (int)(gt & (LPR - 1));
     const long long rowl = gt / LPR;
@@ -362,6 +387,10 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const int nrows, double* par
     const double* __restrict__ x   = a.x;
     const int*    __restrict__ ja  = A.ja;
     const double* __restrict__ val = A.val;
+    const bool               hs    = (A.l2hint & 1) != 0;
+    const bool               hx    = (A.l2hint & 2) != 0;
+    const unsigned long long pol_s = l2_policy(hs ? 1 : 0);
+    const unsigned long long pol_x = l2_policy(hx ? 2 : 0);
     double part = 0.0;
     if (valid) {
         const int ka   = A.ia[row];
@@ -376,15 +405,16 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const int nrows, double* par
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int k = kk + u * LPR;
-                col[u]      = (k < kb) ? ld_stream_i32(ja + k) : -1;
+                col[u]      = (k < kb) ? (hs ? ld_stream_i32_hint(ja + k, pol_s) : ld_stream_i32(ja + k)) : -1;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int k = kk + u * LPR;
-                v[u]        = (PATTERN || k >= kb) ? 1.0 : ld_stream_f64(val + k);
+                v[u]        = (PATTERN || k >= kb) ? 1.0 : (hs ? ld_stream_f64_hint(val + k, pol_s) : ld_stream_f64(val + k));
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) xv[u] = (col[u] >= 0) ? __ldg(x + col[u]) : 0.0;
+            for (int u = 0; u < U; ++u)
+                xv[u] = (col[u] >= 0) ? (hx ? ld_f64_hint(x + col[u], pol_x) : __ldg(x + col[u])) : 0.0;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int k = kk + u * LPR;
@@ -409,6 +439,102 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const int nrows, double* par
             if (want_n2) *a.red.nrm2_out = t[1];
         });
     }
+}
+
+// ------------------------------------------------------------------------------------
+// kernel W ("wide rows"): WPR warps per row (64 / 128 / 256 lanes). The coarse operators of a
+// classical-AMG hierarchy have 400 ... 1400 nonzeros per row and only a few thousand rows (a few
+// hundred per GPU in the multi-GPU solve): with one warp per row the kernel time is a chain of
+// ~10 dependent index->gather rounds; spreading the row over the CTA makes it one or two.
+// Warp partials are combined through shared memory in warp order (deterministic).
+// ------------------------------------------------------------------------------------
+template <int MODE, bool PATTERN, int WPR>
+__global__ void __launch_bounds__(TPB)
+csr_wide_kernel(const CsrView A, const CsrArgs a, const int nrows, double* partials, unsigned int* ticket)
+{
+    constexpr int NW  = TPB / 32;
+    constexpr int RPC = NW / WPR;   // rows per CTA
+    __shared__ double s_part[NW];
+    if (a.done != nullptr && *a.done != 0) return;
+    if (a.hw.mask) {
+        const long long f = (long long)blockIdx.x * RPC;
+        if (a.hw.touches((int)f, (int)(f + RPC))) {
+            if (threadIdx.x == 0) p2p_halo_wait(a.hw);
+            __syncthreads();
+        }
+    }
+    const int       warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int       rl   = warp / WPR, wl = warp - rl * WPR;
+    const long long rowl = (long long)blockIdx.x * RPC + rl;
+    const bool      valid = rowl < nrows;
+    const int       row   = valid ? (int)rowl : 0;
+    const double* __restrict__ x   = a.x;
+    const int*    __restrict__ ja  = A.ja;
+    const double* __restrict__ val = A.val;
+    double part = 0.0;
+    if (valid) {
+        const int ka   = A.ia[row];
+        const int kb   = A.ia[row + 1];
+        const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
+        constexpr int U = 4, STRIDE = 32 * WPR;
+        for (int kk = ka + wl * 32 + lane; kk < kb; kk += U * STRIDE) {
+            int    col[U];
+            double v[U], xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = kk + u * STRIDE;
+                col[u]      = (k < kb) ? ld_stream_i32(ja + k) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = kk + u * STRIDE;
+                v[u]        = (PATTERN || k >= kb) ? 1.0 : ld_stream_f64(val + k);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = (col[u] >= 0) ? __ldg(x + col[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = kk + u * STRIDE;
+                if (k != skip) part += v[u] * xv[u];
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if (lane == 0) s_part[warp] = part;
+    __syncthreads();
+    double red_dot = 0.0, red_n2 = 0.0;
+    const bool want_dot = a.red.dot_out != nullptr;
+    const bool want_n2  = a.red.nrm2_out != nullptr;
+    if (valid && wl == 0 && lane == 0) {
+        double acc = s_part[rl * WPR];
+#pragma unroll
+        for (int w = 1; w < WPR; ++w) acc += s_part[rl * WPR + w];
+        const double out = row_epilogue<MODE>(A, a, row, acc, false);
+        if (want_dot) red_dot = out * a.red.dot_with[row];
+        if (want_n2) red_n2 = out * out;
+    }
+    if (want_dot || want_n2) {
+        double v[2] = {red_dot, red_n2};
+        grid_reduce<2, 0>(v, partials, ticket, [&](const double* t) {
+            if (want_dot) *a.red.dot_out = t[0];
+            if (want_n2) *a.red.nrm2_out = t[1];
+        });
+    }
+}
+
+template <int MODE, bool PATTERN, int WPR>
+static void launch_wide(const DevCSR& A, const CsrView& v, const CsrArgs& a)
+{
+    constexpr int RPC  = (TPB / 32) / WPR;
+    const int     grid = (A.rows + RPC - 1) / RPC;
+    double*       part = nullptr;
+    unsigned int* tick = nullptr;
+    if (a.red.dot_out || a.red.nrm2_out) {
+        part = red_partials((size_t)grid);
+        tick = red_ticket();
+    }
+    FC_LAUNCH((csr_wide_kernel<MODE, PATTERN, WPR>), grid, TPB, 0, v, a, A.rows, part, tick);
 }
 
 template <int MODE, bool PATTERN, int LPR>
@@ -461,6 +587,9 @@ static void launch_pattern(const DevCSR& A, const CsrView& v, const CsrArgs& a)
             case 4: launch_vector<MODE, PATTERN, 4>(A, v, a); return;
             case 8: launch_vector<MODE, PATTERN, 8>(A, v, a); return;
             case 16: launch_vector<MODE, PATTERN, 16>(A, v, a); return;
+            case 64: launch_wide<MODE, PATTERN, 2>(A, v, a); return;
+            case 128: launch_wide<MODE, PATTERN, 4>(A, v, a); return;
+            case 256: launch_wide<MODE, PATTERN, 8>(A, v, a); return;
             default: launch_vector<MODE, PATTERN, 32>(A, v, a); return;
         }
     }
@@ -484,16 +613,17 @@ static void launch_mode(const DevCSR& A, const CsrView& v, const CsrArgs& a)
     else launch_pattern<MODE, false>(A, v, a);
 }
 
-void csr_launch(const DevCSR& A, const CsrArgs& a)
+void csr_launch(const DevCSR& A, const CsrArgs& a_in)
 {
     if (A.rows == 0) return;
-    const bool reads_y = (a.mode == CSR_AXPY || a.mode == CSR_RESID || a.mode >= CSR_JACOBI);
+    const bool reads_y = (a_in.mode == CSR_AXPY || a_in.mode == CSR_RESID || a_in.mode >= CSR_JACOBI);
     double     pbytes  = csr_spmv_bytes(A, reads_y);
-    if (a.mode == CSR_JACOBI || a.mode == CSR_L1) pbytes += 16.0 * A.rows;   // + u read, d read
-    if (a.mode >= CSR_POLY1) pbytes += 16.0 * A.rows;
-    if (A.halo) halo_exchange(*A.halo, const_cast<double*>(a.x));
+    if (a_in.mode == CSR_JACOBI || a_in.mode == CSR_L1) pbytes += 16.0 * A.rows;   // + u read, d read
+    if (a_in.mode >= CSR_POLY1) pbytes += 16.0 * A.rows;
+    CsrArgs a = a_in;
+    if (A.halo) halo_exchange(*A.halo, const_cast<double*>(a.x), &a.hw);
     ProfScope  prof(a.conditional ? a.mode + 50 : a.mode, A.rows, A.nnz, pbytes);
-    CsrView v{A.ia, A.ja, A.val, A.rowblk, A.blkdesc, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap, ctx().opt.rowwise_max};
+    CsrView v{A.ia, A.ja, A.val, A.rowblk, A.blkdesc, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap, ctx().opt.rowwise_max, ctx().opt.l2_hint};
     switch (a.mode) {
         case CSR_MXV: launch_mode<CSR_MXV>(A, v, a); break;
         case CSR_AXPY: launch_mode<CSR_AXPY>(A, v, a); break;
@@ -616,6 +746,11 @@ void csr_upload(DevCSR& d, int rows, int cols, long long nnz, const int* ia, con
     const int vmin    = c.opt.vec_min_avg;
     if (vmin > 0 && avg0 >= vmin)
         d.vec_lpr = c.opt.vec_lpr > 0 ? c.opt.vec_lpr : (avg0 < 48 ? 4 : (avg0 < 96 ? 8 : (avg0 < 384 ? 16 : 32)));
+    // few long rows (coarse levels, above all the per-GPU slabs of a multi-GPU solve): spread a
+    // row over more lanes so that the kernel is not a chain of dependent gather rounds
+    if (d.vec_lpr > 0 && c.opt.vec_lpr <= 0)
+        while (d.vec_lpr < 256 && (long long)rows * d.vec_lpr < c.opt.wide_threads && avg0 / d.vec_lpr >= 8.0)
+            d.vec_lpr *= 2;
     // Rows that go to the vector kernel are summed by lane groups anyway (order differs from the
     // CPU loop by construction), so their entries are sorted by column at upload: consecutive lanes
     // then gather neighbouring x entries and share 32-byte sectors (the unsorted RAP output of

@@ -116,6 +116,8 @@ def bench_main(args):
     log("[bench] rank 0 owns rows [%d, %d) of %d; upload %.2fs" % (r0, r1, n, t_upload))
 
     x_buf = np.zeros(nloc)
+    api.pin_host(b_loc)    # the application's own slices, page-locked once
+    api.pin_host(x_buf)
 
     def host_solve():
         st, x = solver.solve(b_loc, zero, it, out=x_buf)
@@ -192,6 +194,8 @@ def bench_main(args):
             "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": None,
         }
+    api.unpin_host(b_loc)
+    api.unpin_host(x_buf)
     solver.close()
     L.fasp_cuda_comm_finalize()
     return out

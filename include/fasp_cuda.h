@@ -251,6 +251,12 @@ INT fasp_cuda_solver_dbsr_pvfgmres(dBSRmat* A, dvector* b, dvector* x, precond* 
                                    const SHORT restart, const SHORT StopType,
                                    const SHORT PrtLvl);
 
+ /* Page-lock / release an application array (b, x of repeated solves) so that the host-pointer
+ * entry points copy it by DMA instead of staging it. Thin wrappers over cudaHostRegister /
+ * cudaHostUnregister for callers without the CUDA headers; unpin before freeing the array.  */
+INT fasp_cuda_host_pin(void* p, size_t bytes);
+INT fasp_cuda_host_unpin(void* p);
+
 /* ------------------------------------------------------------------------------------ */
 /* Level-5: drivers                                                                       */
 /* ------------------------------------------------------------------------------------ */

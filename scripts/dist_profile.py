@@ -12,6 +12,7 @@ from faspsolver_b200 import api, multigpu as MG, fasp_types as T
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=256)
 ap.add_argument("--agg-rows", type=int, default=200000)
+ap.add_argument("--opts", default="", help="option sets to time before the profile, e.g. 'p2p_fused=1;p2p_fused=0'")
 a = ap.parse_args()
 rank, world, local = MG.init_comm()
 L = api.lib()
@@ -22,12 +23,33 @@ mgl = hf.amg_setup(A, amg)
 s = MG.DistSolver(mgl, amg, agg_rows=a.agg_rows)
 hf.amg_free(mgl, amg)
 bl = np.ascontiguousarray(b[s.row0:s.row1]); z = np.zeros(s.row1 - s.row0)
-for _ in range(3): s.solve(bl, z, it)
+for cfg in [c for c in a.opts.split(";") if c]:
+    for kv in cfg.split(","):
+        k, v = kv.split("=")
+        api.check(L.fasp_cuda_set_option(k.encode(), float(v)))
+    wl = []
+    for _ in range(3):
+        st_, x_ = s.solve(bl, z.copy(), it); wl.append((st_, round(s.stat(2), 2)))
+    MG.barrier()
+    tt = []
+    for _ in range(5):
+        st_, x_ = s.solve(bl, z.copy(), it)
+        tt.append(s.stat(2)); wl.append((st_, round(s.stat(2), 2)))
+    print("[%s] rank %d solves (status, ms): %s" % (cfg, rank, wl), flush=True)
+    import torch.distributed as dist
+    parts = [None] * world
+    dist.all_gather_object(parts, (s.row0, np.array(x_, copy=True)))
+    if rank == 0:
+        full = np.empty(A.shape[0])
+        for p0, xp in parts: full[p0:p0 + xp.size] = xp
+        rel = float(np.linalg.norm(b - A.to_scipy() @ full) / np.linalg.norm(b))
+        print("[%s] world %d agg_rows %d: solve %.3f ms (min %.3f), iterations %d, true relres %.3e" % (cfg, world, a.agg_rows, float(np.mean(tt)), min(tt), st_, rel), flush=True)
+for _ in range(3): s.solve(bl, z.copy(), it)
 MG.barrier()
-t = [s.solve(bl, z, it) and s.stat(2) for _ in range(3)]
+t = [s.solve(bl, z.copy(), it) and s.stat(2) for _ in range(3)]
 L.fasp_cuda_set_option(b"profile", 1.0); L.fasp_cuda_profile_dump(None, 0)
 MG.barrier()
-st, _ = s.solve(bl, z, it)
+st, _ = s.solve(bl, z.copy(), it)
 buf = C.create_string_buffer(64 << 20); L.fasp_cuda_profile_dump(buf, len(buf)); L.fasp_cuda_set_option(b"profile", 0.0)
 recs = [ln.split() for ln in buf.value.decode().splitlines()]
 recs = [(int(k), int(r), int(z_), float(ms)) for k, r, z_, ms, by in recs]

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--ops", default="A,P,R")
     ap.add_argument("--vec-min-avg", type=int, default=-1)
     ap.add_argument("--opt", action="append", default=[], help="library option key=value")
+    ap.add_argument("--lprs", default="", help="comma list of vec_lpr overrides to compare per level (0 = default choice)")
     a = ap.parse_args()
     L = api.lib(); api.check(L.fasp_cuda_init(0))
     for kv in a.opt:
@@ -39,18 +40,20 @@ def main():
         for op in a.ops.split(","):
             if op != "A" and l >= nl - 1: continue
             m = getattr(mgl[l], op)
-            h = L.fasp_cuda_dcsr_upload(C.byref(m))
-            if not h: raise RuntimeError(api.last_error())
-            kernels = [int(k) for k in a.kernels.split(",")] if op == "A" else ([1] if op == "P" else [0])
-            for what in kernels:
-                ms = L.fasp_cuda_dcsr_time_kernel(h, what, a.warm, a.reps, 0)
-                by = 12.0 * m.nnz + 4.0 * (m.row + 1) + 8.0 * m.col + 8.0 * m.row
-                if what in (1, 2): by += 8.0 * m.row
-                if what in (10, 11): by += 24.0 * m.row
-                print(json.dumps({"level": l, "op": op, "rows": m.row, "cols": m.col, "nnz": m.nnz,
-                                  "nnz_per_row": round(m.nnz / max(1, m.row), 1), "kernel": names[what],
-                                  "ms": round(ms, 5), "GBps": round(by / ms * 1e-6, 1)}), flush=True)
-            L.fasp_cuda_dcsr_free(h)
+            for lpr in ([int(v) for v in a.lprs.split(",")] if a.lprs else [None]):
+                if lpr is not None: L.fasp_cuda_set_option(b"vec_lpr", float(lpr))
+                h = L.fasp_cuda_dcsr_upload(C.byref(m))
+                if not h: raise RuntimeError(api.last_error())
+                kernels = [int(k) for k in a.kernels.split(",")] if op == "A" else ([1] if op == "P" else [0])
+                for what in kernels:
+                    ms = L.fasp_cuda_dcsr_time_kernel(h, what, a.warm, a.reps, 0)
+                    by = 12.0 * m.nnz + 4.0 * (m.row + 1) + 8.0 * m.col + 8.0 * m.row
+                    if what in (1, 2): by += 8.0 * m.row
+                    if what in (10, 11): by += 24.0 * m.row
+                    print(json.dumps({"level": l, "op": op, "rows": m.row, "cols": m.col, "nnz": m.nnz,
+                                      "nnz_per_row": round(m.nnz / max(1, m.row), 1), "kernel": names[what], "lpr": lpr,
+                                      "us": round(ms * 1e3, 2), "GBps": round(by / ms * 1e-6, 1)}), flush=True)
+                L.fasp_cuda_dcsr_free(h)
     hf.amg_free(mgl, amg)
 
 if __name__ == "__main__":

@@ -93,3 +93,44 @@ def test_amg_pcg_128_iterations_and_residual(gpu, ref):
     assert abs(relres_reported - 1.3856055505e-09) / 1.3856055505e-09 < 1e-6
     assert hist.size == 13 and np.all(np.diff(hist[1:]) < 0) and abs(hist[-1] - relres_reported) < 1e-5 * relres_reported
     assert np.linalg.norm(b - A.to_scipy() @ x) / np.linalg.norm(b) <= 1e-8
+
+
+def test_repeated_host_solves_with_fresh_and_pinned_buffers(gpu, ref):
+    """The host-pointer solve must not depend on the identity of the caller's arrays: every call gets
+    newly allocated (mmap-sized) numpy arrays that are released afterwards, so a remembered
+    page-lock registration would go stale. Then the same with arrays the application pinned itself
+    through fasp_cuda_host_pin (DMA path), and after unpinning them again."""
+    A = PB.poisson7(48)
+    n = A.shape[0]
+    S = A.to_scipy()
+    amg = ref.amg_param(print_level=0, smoother=T.SMOOTHER_L1DIAG)
+    it = ref.its_param(itsolver_type=T.SOLVER_CG, tol=1e-8, maxit=100, print_level=0)
+    mgl = ref.amg_setup(A, amg)
+    try:
+        s = api.KrylovAmgSolver(mgl, amg)
+        rng = np.random.default_rng(5)
+        counts = []
+        for k in range(6):
+            b = rng.uniform(0.5, 1.5, n)
+            junk = [np.empty(n) for _ in range(k % 3)]      # perturb the allocator between calls
+            st, x = s.solve(b, np.zeros(n), it)
+            assert st > 0, (k, st, api.last_error())
+            assert np.linalg.norm(b - S @ x) / np.linalg.norm(b) <= 1e-8 * 1.001, k
+            counts.append(st)
+            del b, x, junk
+        assert max(counts) - min(counts) <= 1
+        b, out = rng.uniform(0.5, 1.5, n), np.zeros(n)
+        api.pin_host(b); api.pin_host(out)
+        api.pin_host(out)                                    # pinning twice is not an error
+        for _ in range(2):
+            st, x = s.solve(b, np.zeros(n), it, out=out)
+            assert st > 0 and x is out
+            assert np.linalg.norm(b - S @ out) / np.linalg.norm(b) <= 1e-8 * 1.001
+        api.unpin_host(b); api.unpin_host(out)
+        st, x = s.solve(b, np.zeros(n), it, out=out)
+        assert st > 0 and np.linalg.norm(b - S @ out) / np.linalg.norm(b) <= 1e-8 * 1.001
+        with pytest.raises(api.FaspCudaError):
+            api.unpin_host(out)                              # not pinned any more
+        s.close()
+    finally:
+        ref.amg_free(mgl, amg)

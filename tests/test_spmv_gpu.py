@@ -115,3 +115,34 @@ def test_empty_and_tiny(gpu):
     x = np.array([1.0, 2.0, 3.0])
     assert gpu.fasp_cuda_blas_dcsr_mxv(A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
     assert np.array_equal(y, [0.0, 7.5, 0.0])
+
+
+@pytest.mark.parametrize("lpr", [32, 64, 128, 256])
+def test_wide_row_kernels(gpu, ref, data, lpr):
+    """Rows spread over one warp (32 lanes) or 2 / 4 / 8 warps (csr_wide_kernel): SpMV, aAxpy and an
+    L1 sweep on matrices with 1000 ... 8000 nonzeros per row, same bound as every other kernel."""
+    rng = np.random.default_rng(21)
+    sq = sp.random(300, 300, density=0.6, format="csr", random_state=9) + sp.eye(300) * 40.0
+    mats = [A for nm, A in _cases(data) if nm in ("longrow", "rows1000", "irregular")] + [CSR.from_scipy(sq.tocsr())]
+    gpu.fasp_cuda_set_option(b"vec_min_avg", 1.0)
+    gpu.fasp_cuda_set_option(b"vec_lpr", float(lpr))
+    try:
+        for A in mats:
+            x = rng.uniform(-1, 1, A.shape[1])
+            y = np.empty(A.shape[0])
+            assert gpu.fasp_cuda_blas_dcsr_mxv(A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
+            assert np.all(np.abs(y - ref.mxv(A, x)) <= 1e-14 * _bound(A, x) + 1e-300)
+            y0 = rng.uniform(-1, 1, A.shape[0])
+            y = y0.copy()
+            assert gpu.fasp_cuda_blas_dcsr_aAxpy(-1.0, A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
+            assert np.all(np.abs(y - ref.aAxpy(-1.0, A, x, y0)) <= 1e-14 * (_bound(A, x) + np.abs(y0)) + 1e-300)
+        A = mats[-1]
+        n = A.shape[0]
+        b, u0 = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+        vb, u, ur = T.Vec(b), T.Vec(u0.copy()), T.Vec(u0.copy())
+        assert gpu.fasp_cuda_smoother_dcsr_L1diag(u.ptr(), 0, n - 1, 1, A.ptr(), vb.ptr(), 2) == 0
+        ref.L.fasp_smoother_dcsr_L1diag(ur.ptr(), 0, n - 1, 1, A.ptr(), vb.ptr(), 2)
+        assert np.abs(u.a - ur.a).max() <= 1e-12 * max(1.0, np.abs(ur.a).max())
+    finally:
+        gpu.fasp_cuda_set_option(b"vec_lpr", 0.0)
+        gpu.fasp_cuda_set_option(b"vec_min_avg", 24.0)
