@@ -164,8 +164,6 @@ static int* option_slot(const char* key)
     if (!strcmp(key, "sort_rows")) return &o.sort_rows;
     if (!strcmp(key, "host_register")) return &o.host_register;
     if (!strcmp(key, "rowwise_max")) return &o.rowwise_max;
-    if (!strcmp(key, "l2_hint")) return &o.l2_hint;
-    if (!strcmp(key, "p2p_fused")) return &o.p2p_fused;
     if (!strcmp(key, "wide_threads")) return &o.wide_threads;
     if (!strcmp(key, "vec_lpr")) return &o.vec_lpr;
     if (!strcmp(key, "gs_multicolor")) return &o.gs_multicolor;

@@ -62,11 +62,8 @@ struct Options {
     int    sort_rows        = 1;   // sort the entries of vector-kernel rows by column at upload
     int    pipe_cap_mult    = 8;   // row-block capacity <= this many nonzeros per thread
     int    pipe_tpb         = 128; // its threads per CTA = max rows per row block (64/128/256)
-    int    p2p_fused        = 0;   // multi-GPU ghost exchange: 0 push + all-to-all barrier kernel (fastest measured),
-                                   // 1 push+signal kernel and consumer-side wait, 2 push + barrier with the partners only
     int    wide_threads     = 400000; // long rows: double the lanes per row (up to 256 = csr_wide_kernel) while
                                       // rows x lanes stays below this and a lane keeps >= 8 entries
-    int    l2_hint          = 0;   // bit 0: matrix stream L2 evict_first, bit 1: gathered vector L2 evict_last
     int    rowwise_max      = 32;  // blocks averaging <= this many nonzeros per row: one thread per row
     int    vec_lpr          = 0;   // > 0: force this many lanes per row in the vector kernel
     int    gs_multicolor    = 0;   // accept SMOOTHER_GS in the cycle as multicolour GS (OpenMP-FASP semantics)
@@ -192,8 +189,7 @@ struct Reduce {
 // all-reduce the outputs of a fused reduction when it is global and a communicator is active
 void reduce_finish(const Reduce& red);
 // ghost exchange (dist.cu); x must have room for the plan's ghosts behind its owned entries
-struct HaloWait;
-void halo_exchange(const HaloPlan& h, double* x, HaloWait* wait = nullptr);
+void halo_exchange(const HaloPlan& h, double* x);
 
 // ------------------------------------------------------------------------------------
 // CSR row kernels (spmv.cu)
@@ -207,25 +203,6 @@ enum CsrMode {
     CSR_POLY1 = 5,   // poly smoother first step  (see spmv.cu)
     CSR_POLYJ = 6,   // poly smoother recurrence step
     CSR_RESID_DINV = 7  // y = b - A x ; aux_out = dinv .* y   (poly smoother residual)
-};
-
-// Multi-GPU, peer-memory path: the consumer kernel itself waits (one thread per CTA) until the
-// ranks in `mask` have announced ghost data of exchange number *seq in flags[] (p2p.cu).
-struct HaloWait {
-    const unsigned long long* flags = nullptr;
-    const unsigned long long* seq   = nullptr;
-    int*                      err   = nullptr;
-    unsigned int              mask  = 0;
-    // only rows inside these (<= 4) intervals reference ghost columns: the CTAs that own other
-    // rows never wait, so the interior of the slab overlaps the exchange
-    int nint = 0;
-    int lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
-    __host__ __device__ bool touches(int r0, int r1) const
-    {
-        for (int i = 0; i < nint; ++i)
-            if (r0 < hi[i] && r1 > lo[i]) return true;
-        return false;
-    }
 };
 
 struct CsrArgs {
@@ -243,7 +220,6 @@ struct CsrArgs {
     Reduce        red;
     const int*    done = nullptr;
     bool          conditional = false;   // launch gated by a rarely-taken branch flag (profiling tag)
-    HaloWait      hw;                    // filled by csr_launch when the ghosts arrive by peer stores
 };
 void csr_launch(const DevCSR& A, const CsrArgs& a);
 

@@ -34,10 +34,10 @@ __global__ void k_halo_pack(int n, const int* __restrict__ idx, const double* __
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) buf[i] = x[idx[i]];
 }
 
-void halo_exchange(const HaloPlan& h, double* x, HaloWait* wait)
+void halo_exchange(const HaloPlan& h, double* x)
 {
     if (!comm_active()) return;
-    if (p2p_halo_exchange(h, x, wait)) return;   // peer-memory push (+ device barrier or consumer-side wait)
+    if (p2p_halo_exchange(h, x)) return;   // peer-memory push + device barrier
     if (h.nsend == 0 && h.nghost == 0) return;
     ProfScope prof(400, h.nloc, h.nsend + h.nghost, 8.0 * (h.nsend + h.nghost));
     if (h.nsend > 0) {
@@ -149,25 +149,6 @@ static HaloPlan* make_plan(const dCSRmat& A, const std::vector<int>& roff, const
         h->recv_peer.push_back(q);
         h->recv_off.push_back((int)b);
         h->recv_cnt.push_back((int)(g - b));
-    }
-    {   // rows that read ghosts: maximal runs, the closest ones merged until at most 4 remain
-        std::vector<std::pair<int, int>> runs;
-        for (int i = 0; i < loc.rows; ++i) {
-            bool g = false;
-            for (int k = loc.ia[i]; k < loc.ia[i + 1] && !g; ++k) g = loc.ja[k] >= h->nloc;
-            if (!g) continue;
-            if (!runs.empty() && i - runs.back().second < 1024) runs.back().second = i + 1;
-            else runs.push_back({i, i + 1});
-        }
-        while (runs.size() > 4) {
-            size_t best = 1;
-            for (size_t r = 2; r < runs.size(); ++r)
-                if (runs[r].first - runs[r - 1].second < runs[best].first - runs[best - 1].second) best = r;
-            runs[best - 1].second = runs[best].second;
-            runs.erase(runs.begin() + best);
-        }
-        h->ngrow = (int)runs.size();
-        for (int r = 0; r < h->ngrow; ++r) h->grow_lo[r] = runs[r].first, h->grow_hi[r] = runs[r].second;
     }
     std::vector<std::vector<int>> send;
     dist_send_lists(A, roff, coff, rank, send);

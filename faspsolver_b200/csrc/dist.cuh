@@ -18,9 +18,6 @@ struct HaloPlan {
     // peer-memory path (p2p.cu): where each send segment lands inside the peer's vector
     bool             p2p_ready = false;
     std::vector<int> peer_dst_off;
-    // local row intervals [lo, hi) that contain every row referencing a ghost column (<= 4)
-    int ngrow = 0;
-    int grow_lo[4] = {0, 0, 0, 0}, grow_hi[4] = {0, 0, 0, 0};
 };
 void halo_free(HaloPlan* h);
 

@@ -14,11 +14,6 @@ struct P2PCtrl {
     double             slots[2][P2P_MAX_RANKS][4];   // all-reduce partials, double-buffered by epoch parity
     unsigned long long epoch;                        // my barrier counter (device-resident: graph replays advance it)
     int                error;                        // spin budget exceeded
-    // fused ghost exchange (k_halo_push_signal + consumer-side wait): point-to-point, neighbours only
-    unsigned long long dflags[P2P_MAX_RANKS];        // dflags[q] = last exchange number whose ghosts rank q stored here
-    unsigned long long acks[P2P_MAX_RANKS];          // acks[q]   = rank q has consumed all exchanges <= this number
-    unsigned long long seq;                          // my exchange counter
-    unsigned int       ticket;                       // last-CTA detection of the push kernel
 };
 
 namespace {
@@ -34,11 +29,6 @@ struct State {
     P2PCtrl* peer_ctrl[P2P_MAX_RANKS] = {nullptr};
     std::vector<Region> regions;
     const void* last_exchanged = nullptr;   // a vector must not be pushed into twice in a row
-    // fused protocol: what the previous exchange looked like (decides which peers must acknowledge)
-    const void*  fused_prev_x    = nullptr;
-    unsigned int fused_prev_recv = 0;
-    bool         fused_synced    = false;   // an all-to-all barrier ran since the previous exchange
-    unsigned int prev_partners   = 0;       // neighbour-barrier mode: ranks the previous exchange synchronised with
 };
 State& S()
 {
@@ -52,15 +42,7 @@ constexpr long long SPIN_BUDGET = 4000000000LL;   // ~2 s of SM clocks
 } // namespace
 
 bool p2p_active() { return S().on; }
-void p2p_reset_order_hook()
-{
-    State& s          = S();
-    s.last_exchanged  = nullptr;
-    s.fused_prev_x    = nullptr;
-    s.fused_prev_recv = 0;
-    s.fused_synced    = false;
-    s.prev_partners   = 0;
-}
+void p2p_reset_order_hook() { S().last_exchanged = nullptr; }
 
 // all-gather of a fixed-size byte blob per rank through NCCL (setup only)
 static void allgather_bytes(const void* mine, size_t bytes, std::vector<char>& all)
@@ -116,7 +98,7 @@ void p2p_allgather_ints(const std::vector<int>& mine, std::vector<int>& all)
     all.resize(mine.size() * comm_size());
     memcpy(all.data(), bytes.data(), bytes.size());
 }
-void p2p_reset_order() { p2p_reset_order_hook(); }
+void p2p_reset_order() { S().last_exchanged = nullptr; }
 int  p2p_error()
 {
     State& s = S();
@@ -221,8 +203,7 @@ __device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long
 }
 
 // one CTA, one thread per rank: announce my next epoch to everybody, wait for everybody's
-__device__ __forceinline__ unsigned long long barrier_body(P2PCtrl* me, const PeerCtrls& peers, int rank, int n,
-                                                           unsigned int mask = 0xffffffffu)
+__device__ __forceinline__ unsigned long long barrier_body(P2PCtrl* me, const PeerCtrls& peers, int rank, int n)
 {
     __shared__ unsigned long long s_e;
     const int q = threadIdx.x;
@@ -230,7 +211,7 @@ __device__ __forceinline__ unsigned long long barrier_body(P2PCtrl* me, const Pe
     __syncthreads();
     const unsigned long long e = s_e;
     __threadfence_system();   // my earlier stores to peer memory are ordered before the flag
-    if (q < n && ((mask >> q) & 1u)) {
+    if (q < n) {
         st_sys(&peers.p[q]->flags[rank], e);
         const long long t0 = clock64();
         while (ld_sys(&me->flags[q]) < e) {
@@ -246,10 +227,7 @@ __device__ __forceinline__ unsigned long long barrier_body(P2PCtrl* me, const Pe
     return e;
 }
 
-__global__ void k_p2p_barrier(P2PCtrl* me, PeerCtrls peers, int rank, int n, unsigned int mask)
-{
-    barrier_body(me, peers, rank, n, mask);
-}
+__global__ void k_p2p_barrier(P2PCtrl* me, PeerCtrls peers, int rank, int n) { barrier_body(me, peers, rank, n); }
 
 struct PushDst {
     double* dst[P2P_MAX_RANKS];   // per send segment: where it lands in the peer's vector
@@ -263,64 +241,6 @@ k_halo_push(int n, const int* __restrict__ idx, const double* __restrict__ x, Pu
         int s = 0;
         while (s + 1 < d.nseg && i >= d.off[s + 1]) ++s;
         d.dst[s][i - d.off[s]] = x[idx[i]];
-    }
-}
-
-// Fused ghost exchange, exchange number s = seq + 1 (every rank runs the same sequence):
-//   1. tell the ranks that push to me that everything up to s-1 has been consumed here (all my
-//      earlier kernels are complete: stream order);
-//   2. make sure the receivers' ghost regions may be overwritten. For a receiver q that also SENT
-//      to me in exchange s-1 (`throttle_mask`) it is enough to see its data flag of s-1 (a local
-//      poll, normally long satisfied): q finished its push s-1, hence its consumer s-2 and all
-//      earlier ones, and the host only puts q into this mask when exchange s targets a different
-//      vector than s-1 -- the one q may still be reading. Every other receiver (`ack_mask`) must
-//      have acknowledged s-1 (step 1 on its side); that handshake is off the critical path in the
-//      common case and is skipped altogether right after an all-to-all barrier;
-//   3. store my boundary entries straight into the peers' ghost regions;
-//   4. the last CTA (ticket) publishes s in the receivers' dflags and advances seq.
-// The consumer kernel waits for dflags[q] >= seq from its senders (p2p_halo_wait), only in the
-// CTAs whose rows read ghosts. No ghost entry is overwritten before its reader has finished or
-// read before it has arrived.
-__global__ void __launch_bounds__(256)
-k_halo_push_signal(P2PCtrl* me, PeerCtrls peers, int rank, int nranks, unsigned int send_mask,
-                   unsigned int recv_mask, unsigned int ack_mask, unsigned int throttle_mask, int n,
-                   const int* __restrict__ idx, const double* __restrict__ x, PushDst d)
-{
-    __shared__ int           s_last;
-    const unsigned long long s = me->seq + 1;
-    const int                q = threadIdx.x;
-    if (q < nranks) {
-        if (blockIdx.x == 0 && ((recv_mask >> q) & 1u)) st_sys(&peers.p[q]->acks[rank], s - 1);
-        const bool wa = (ack_mask >> q) & 1u, wt = (throttle_mask >> q) & 1u;
-        if (wa || wt) {
-            const unsigned long long* w  = wa ? &me->acks[q] : &me->dflags[q];
-            const long long           t0 = clock64();
-            while (ld_sys(w) < s - 1) {
-                if (clock64() - t0 > SPIN_BUDGET) {
-                    me->error = 1;
-                    break;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int sg = 0;
-        while (sg + 1 < d.nseg && i >= d.off[sg + 1]) ++sg;
-        d.dst[sg][i - d.off[sg]] = x[idx[i]];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();   // the CTA's stores (ordered before by the barrier) precede the ticket / the flag
-        s_last = (atomicAdd(&me->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-        if (s_last) __threadfence_system();
-    }
-    __syncthreads();
-    if (!s_last) return;
-    if (q < nranks && ((send_mask >> q) & 1u)) st_sys(&peers.p[q]->dflags[rank], s);
-    if (q == 0) {
-        me->ticket = 0;
-        me->seq    = s;
     }
 }
 
@@ -365,70 +285,20 @@ void p2p_barrier()
 {
     State& s = S();
     if (!s.on) return;
-    FC_LAUNCH(k_p2p_barrier, 1, 32, 0, s.ctrl, peer_ctrls(), s.rank, s.size, 0xffffffffu);
-    s.fused_synced  = true;
-    s.prev_partners = 0xffffffffu;
+    FC_LAUNCH(k_p2p_barrier, 1, 32, 0, s.ctrl, peer_ctrls(), s.rank, s.size);
 }
 
-// barrier with the exchange partners only (the epoch still advances on every rank)
-static void p2p_barrier_masked(unsigned int mask)
-{
-    State& s = S();
-    FC_LAUNCH(k_p2p_barrier, 1, 32, 0, s.ctrl, peer_ctrls(), s.rank, s.size, mask);
-}
-
-bool p2p_halo_exchange(const HaloPlan& h, double* x, HaloWait* wait)
+bool p2p_halo_exchange(const HaloPlan& h, double* x)
 {
     State& s = S();
     if (!s.on || !h.p2p_ready) return false;
     double* peer[P2P_MAX_RANKS];
     if (!p2p_lookup(x, peer)) return false;
     ProfScope prof(400, h.nloc, h.nsend + h.nghost, 8.0 * (h.nsend + h.nghost));
-    if (wait && ctx().opt.p2p_fused == 1) {
-        unsigned int send_mask = 0, recv_mask = 0;
-        PushDst      d;
-        d.nseg = (int)h.send_peer.size();
-        for (int k = 0; k < d.nseg; ++k) {
-            d.dst[k] = peer[h.send_peer[k]] + h.peer_dst_off[k];
-            d.off[k] = h.send_off[k];
-            send_mask |= 1u << h.send_peer[k];
-        }
-        d.off[d.nseg] = h.nsend;
-        for (int q : h.recv_peer) recv_mask |= 1u << q;
-        // always launched, even without neighbours: the exchange counter must advance in lockstep
-        int g = (h.nsend + 255) / 256;
-        if (g > 592) g = 592;
-        if (g < 1) g = 1;
-        unsigned int throttle = 0, ack = send_mask;
-        if (s.fused_synced) {
-            ack = 0;   // every rank passed a barrier after its last consumer
-        } else if (s.fused_prev_x != nullptr && s.fused_prev_x != x) {
-            throttle = send_mask & s.fused_prev_recv;
-            ack      = send_mask & ~throttle;
-        }
-        s.fused_prev_x    = x;
-        s.fused_prev_recv = recv_mask;
-        s.fused_synced    = false;
-        FC_LAUNCH(k_halo_push_signal, g, 256, 0, s.ctrl, peer_ctrls(), s.rank, s.size, send_mask, recv_mask,
-                  ack, throttle, h.nsend, h.send_idx, x, d);
-        wait->flags = s.ctrl->dflags;
-        wait->seq   = &s.ctrl->seq;
-        wait->err   = &s.ctrl->error;
-        wait->mask  = recv_mask;
-        wait->nint  = h.ngrow;
-        for (int i = 0; i < h.ngrow; ++i) wait->lo[i] = h.grow_lo[i], wait->hi[i] = h.grow_hi[i];
-        s.last_exchanged = nullptr;   // the next barrier-protocol user starts with a barrier
-        return true;
-    }
     // the previous exchange's barrier only guarantees that every rank finished the kernel BEFORE it;
     // pushing into the vector that kernel is still reading on a slower rank needs one more barrier
-    unsigned int partners = 0;
-    for (int q : h.send_peer) partners |= 1u << q;
-    for (int q : h.recv_peer) partners |= 1u << q;
-    const bool nb = ctx().opt.p2p_fused == 2;   // barrier with the exchange partners only
-    if (s.last_exchanged == x || s.last_exchanged == nullptr || (nb && (partners & ~s.prev_partners))) p2p_barrier();
+    if (s.last_exchanged == x || s.last_exchanged == nullptr) p2p_barrier();
     s.last_exchanged = x;
-    s.prev_partners  = nb ? partners : 0xffffffffu;
     if (h.nsend > 0) {
         PushDst d;
         d.nseg = (int)h.send_peer.size();
@@ -441,8 +311,7 @@ bool p2p_halo_exchange(const HaloPlan& h, double* x, HaloWait* wait)
         if (g > 592) g = 592;
         FC_LAUNCH(k_halo_push, g, 256, 0, h.nsend, h.send_idx, x, d);
     }
-    if (nb) p2p_barrier_masked(partners);
-    else p2p_barrier();
+    p2p_barrier();
     return true;
 }
 
@@ -451,7 +320,6 @@ void p2p_allreduce(double* buf, int count, int op)
     State& s = S();
     ProfScope prof(401, count, 0, 8.0 * count);
     FC_LAUNCH(k_p2p_allreduce, 1, 32, 0, s.ctrl, peer_ctrls(), s.rank, s.size, buf, count, op);
-    s.fused_synced = true;
 }
 
 bool p2p_allgatherv(double* full, const std::vector<size_t>& counts, const std::vector<size_t>& displs)
@@ -461,8 +329,7 @@ bool p2p_allgatherv(double* full, const std::vector<size_t>& counts, const std::
     double* peer[P2P_MAX_RANKS];
     if (!p2p_lookup(full, peer)) return false;
     ProfScope prof(402, (int)counts[s.rank], 0, 8.0 * counts[s.rank]);
-    // neighbour-only exchange barriers leave non-neighbours unsynchronised: meet everybody first
-    if (s.last_exchanged == full || s.last_exchanged == nullptr || ctx().opt.p2p_fused == 2) p2p_barrier();
+    if (s.last_exchanged == full || s.last_exchanged == nullptr) p2p_barrier();
     s.last_exchanged = full;
     GatherDst d;
     d.n = 0;

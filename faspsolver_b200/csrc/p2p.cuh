@@ -32,30 +32,7 @@ void p2p_allgather_ints(const std::vector<int>& mine, std::vector<int>& all);
 void p2p_reset_order();   // forget the last exchanged vector (start of a captured graph)
 int  p2p_error();         // nonzero if a device-side wait ran out of its spin budget
 // push-based ghost exchange + barrier; returns false if x is not peer-mapped (caller uses NCCL)
-// With `wait` given (and option p2p_fused) the push kernel also signals the receivers and the
-// CONSUMER kernel waits for the data itself (HaloWait): one launch per exchange.
-bool p2p_halo_exchange(const HaloPlan& h, double* x, HaloWait* wait = nullptr);
-// device-side wait used by the consumer kernels (spmv.cu)
-__device__ __forceinline__ void p2p_halo_wait(const HaloWait& w)
-{
-    const unsigned long long s = *reinterpret_cast<const volatile unsigned long long*>(w.seq);
-    unsigned int             m = w.mask;
-    while (m) {
-        const int q = __ffs((int)m) - 1;
-        m &= m - 1;
-        const long long    t0 = clock64();
-        unsigned long long v;
-        for (;;) {
-            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w.flags + q) : "memory");
-            if (v >= s) break;
-            if (clock64() - t0 > 4000000000LL) {   // ~2 s: raise the error word instead of hanging
-                *w.err = 1;
-                break;
-            }
-        }
-    }
-    __threadfence_system();   // acquire: the ghost entries are read after the flags
-}
+bool p2p_halo_exchange(const HaloPlan& h, double* x);
 // in-place all-reduce of <= 4 doubles (op 0 sum, 2 max)
 void p2p_allreduce(double* buf, int count, int op);
 // every rank's slice [displs[r], +counts[r]) of `full` is filled from its owner

@@ -40,42 +40,5 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned in
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
-// L2 eviction policies (createpolicy): the streamed matrix slices are read once and should leave
-// L2 first; the gathered vector is re-read by neighbouring rows and should stay
-__device__ __forceinline__ unsigned long long l2_policy(int kind)   // 0 normal, 1 evict_first, 2 evict_last
-{
-    unsigned long long p;
-    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsigned int bytes,
-                                              unsigned long long* bar, unsigned long long policy)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-        : "memory");
-}
-__device__ __forceinline__ double ld_f64_hint(const double* p, unsigned long long policy)
-{
-    double v;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
-    return v;
-}
-__device__ __forceinline__ double ld_stream_f64_hint(const double* p, unsigned long long policy)
-{
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
-    return v;
-}
-__device__ __forceinline__ int ld_stream_i32_hint(const int* p, unsigned long long policy)
-{
-    int v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
-    return v;
-}
 
 } // namespace fc

@@ -21,7 +21,6 @@
 #include "common.cuh"
 #include "reduce.cuh"
 #include "pipe.cuh"
-#include "p2p.cuh"
 #include <algorithm>
 #include <thread>
 
@@ -42,7 +41,6 @@ struct CsrView {
     const double* dinv;
     int           cap;
     int           rowwise_max;
-    int           l2hint;   // bit 0: matrix stream evict_first, bit 1: gathered vector evict_last
 };
 
 __device__ __forceinline__ int ld_stream_i32(const int* p)
@@ -167,10 +165,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
     auto st_ia  = [&](int s) { return st_ja(s) + cap + 8; };
     const int2* __restrict__ desc = A.blkdesc;   // desc[b] = {first row, ia[first row]}
     const double* __restrict__ x  = a.x;
-    const bool               hx    = (A.l2hint & 2) != 0;
-    const unsigned long long pol_s = l2_policy((A.l2hint & 1) ? 1 : 0);
-    const unsigned long long pol_x = l2_policy(hx ? 2 : 0);
-    auto gx = [&](int col) { return hx ? ld_f64_hint(x + col, pol_x) : __ldg(x + col); };
+    auto gx = [&](int col) { return __ldg(x + col); };
 
     // thread 0 is the producer: one mbarrier arrival (+ the bulk-copy byte count) per stage use
     auto issue = [&](int blk, int s) {
@@ -183,15 +178,9 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
             const int          r0a = m.r0 & ~3;
             const unsigned int nra = (unsigned int)(((m.r0 + m.nrows + 1 + 3) & ~3) - r0a);
             mbar_expect_tx(&s_bar[s], na * 4u + (PATTERN ? 0u : na * 8u) + nra * 4u);
-            if (A.l2hint & 1) {
-                if (na) bulk_g2s_hint(st_ja(s), A.ja + k0a, na * 4u, &s_bar[s], pol_s);
-                if (!PATTERN && na) bulk_g2s_hint(st_val(s), A.val + k0a, na * 8u, &s_bar[s], pol_s);
-                bulk_g2s_hint(st_ia(s), A.ia + r0a, nra * 4u, &s_bar[s], pol_s);
-            } else {
-                if (na) bulk_g2s(st_ja(s), A.ja + k0a, na * 4u, &s_bar[s]);
-                if (!PATTERN && na) bulk_g2s(st_val(s), A.val + k0a, na * 8u, &s_bar[s]);
-                bulk_g2s(st_ia(s), A.ia + r0a, nra * 4u, &s_bar[s]);
-            }
+            if (na) bulk_g2s(st_ja(s), A.ja + k0a, na * 4u, &s_bar[s]);
+            if (!PATTERN && na) bulk_g2s(st_val(s), A.val + k0a, na * 8u, &s_bar[s]);
+            bulk_g2s(st_ia(s), A.ia + r0a, nra * 4u, &s_bar[s]);
         } else {
             mbar_expect_tx(&s_bar[s], 0u);   // long row: handled from global memory
         }
@@ -207,7 +196,6 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
         }
     }
     __syncthreads();
-    bool halo_pending = a.hw.mask != 0;   // multi-GPU: wait for the peers' ghost entries lazily
 
     double     red_dot = 0.0, red_n2 = 0.0;
     const bool want_dot = a.red.dot_out != nullptr;
@@ -218,11 +206,6 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
         mbar_wait(&s_bar[s], (unsigned int)ph);
         const PipeMeta m = s_meta[s];
         const int r0 = m.r0, nrows = m.nrows, k0 = m.k0, n = m.n;
-        if (halo_pending && a.hw.touches(r0, r0 + nrows)) {   // first block of this CTA that reads ghosts
-            if (tid == 0) p2p_halo_wait(a.hw);
-            __syncthreads();
-            halo_pending = false;
-        }
         if (n <= cap) {
             double*    sp  = st_val(s) + (k0 & 3);
             const int* sj  = st_ja(s) + (k0 & 3);
@@ -372,13 +355,6 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const int nrows, double* par
                   unsigned int* ticket)
 {
     if (a.done != nullptr && *a.done != 0) return;
-    if (a.hw.mask) {
-        const long long f = (long long)blockIdx.x * (TPB / LPR);
-        if (a.hw.touches((int)f, (int)(f + TPB / LPR))) {
-            if (threadIdx.x == 0) p2p_halo_wait(a.hw);
-            __syncthreads();
-        }
-    }
     const long long gt   = (long long)blockIdx.x * TPB + threadIdx.x;
     const int       lane = (int)(gt & (LPR - 1));
     const long long rowl = gt / LPR;
@@ -387,10 +363,6 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const int nrows, double* par
     const double* __restrict__ x   = a.x;
     const int*    __restrict__ ja  = A.ja;
     const double* __restrict__ val = A.val;
-    const bool               hs    = (A.l2hint & 1) != 0;
-    const bool               hx    = (A.l2hint & 2) != 0;
-    const unsigned long long pol_s = l2_policy(hs ? 1 : 0);
-    const unsigned long long pol_x = l2_policy(hx ? 2 : 0);
     double part = 0.0;
     if (valid) {
         const int ka   = A.ia[row];
@@ -405,16 +377,15 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const int nrows, double* par
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int k = kk + u * LPR;
-                col[u]      = (k < kb) ? (hs ? ld_stream_i32_hint(ja + k, pol_s) : ld_stream_i32(ja + k)) : -1;
+                col[u]      = (k < kb) ? ld_stream_i32(ja + k) : -1;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int k = kk + u * LPR;
-                v[u]        = (PATTERN || k >= kb) ? 1.0 : (hs ? ld_stream_f64_hint(val + k, pol_s) : ld_stream_f64(val + k));
+                v[u]        = (PATTERN || k >= kb) ? 1.0 : ld_stream_f64(val + k);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                xv[u] = (col[u] >= 0) ? (hx ? ld_f64_hint(x + col[u], pol_x) : __ldg(x + col[u])) : 0.0;
+            for (int u = 0; u < U; ++u) xv[u] = (col[u] >= 0) ? __ldg(x + col[u]) : 0.0;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int k = kk + u * LPR;
@@ -456,13 +427,6 @@ csr_wide_kernel(const CsrView A, const CsrArgs a, const int nrows, double* parti
     constexpr int RPC = NW / WPR;   // rows per CTA
     __shared__ double s_part[NW];
     if (a.done != nullptr && *a.done != 0) return;
-    if (a.hw.mask) {
-        const long long f = (long long)blockIdx.x * RPC;
-        if (a.hw.touches((int)f, (int)(f + RPC))) {
-            if (threadIdx.x == 0) p2p_halo_wait(a.hw);
-            __syncthreads();
-        }
-    }
     const int       warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int       rl   = warp / WPR, wl = warp - rl * WPR;
     const long long rowl = (long long)blockIdx.x * RPC + rl;
@@ -620,10 +584,10 @@ void csr_launch(const DevCSR& A, const CsrArgs& a_in)
     double     pbytes  = csr_spmv_bytes(A, reads_y);
     if (a_in.mode == CSR_JACOBI || a_in.mode == CSR_L1) pbytes += 16.0 * A.rows;   // + u read, d read
     if (a_in.mode >= CSR_POLY1) pbytes += 16.0 * A.rows;
-    CsrArgs a = a_in;
-    if (A.halo) halo_exchange(*A.halo, const_cast<double*>(a.x), &a.hw);
+    const CsrArgs& a = a_in;
+    if (A.halo) halo_exchange(*A.halo, const_cast<double*>(a.x));
     ProfScope  prof(a.conditional ? a.mode + 50 : a.mode, A.rows, A.nnz, pbytes);
-    CsrView v{A.ia, A.ja, A.val, A.rowblk, A.blkdesc, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap, ctx().opt.rowwise_max, ctx().opt.l2_hint};
+    CsrView v{A.ia, A.ja, A.val, A.rowblk, A.blkdesc, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap, ctx().opt.rowwise_max};
     switch (a.mode) {
         case CSR_MXV: launch_mode<CSR_MXV>(A, v, a); break;
         case CSR_AXPY: launch_mode<CSR_AXPY>(A, v, a); break;
