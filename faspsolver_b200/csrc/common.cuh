@@ -54,17 +54,18 @@ struct Options {
     int    graph            = 1;
     int    zero_guess       = 1;
     int    lookahead        = 2;   // Krylov iterations enqueued ahead of the status read
-    int    vec_min_avg      = 24;  // rows averaging >= this many nonzeros use the vector kernel
+    int    vec_min_avg      = 48;  // rows averaging >= this many nonzeros use the vector kernel
     int    pipe             = 1;   // stream kernel: persistent TMA-pipelined variant
     int    pipe_ctas        = 8;   // its CTAs per SM (upper bound)
     int    pipe_stages      = 2;   // its shared-memory stages per CTA
     int    host_register    = 1;   // 2: page-lock unknown caller buffers in place and remember them (see solver.cu)
     int    sort_rows        = 1;   // sort the entries of vector-kernel rows by column at upload
-    int    pipe_cap_mult    = 8;   // row-block capacity <= this many nonzeros per thread
+    int    pipe_cap_mult    = 16;   // row-block capacity <= this many nonzeros per thread
     int    pipe_tpb         = 128; // its threads per CTA = max rows per row block (64/128/256)
     int    wide_threads     = 400000; // long rows: double the lanes per row (up to 256 = csr_wide_kernel) while
                                       // rows x lanes stays below this and a lane keeps >= 8 entries
-    int    rowwise_max      = 32;  // blocks averaging <= this many nonzeros per row: one thread per row
+    int    gather16_min_avg = 6;   // pipelined kernel: rows averaging >= this use the 16-deep gather variant (0 = never)
+    int    rowwise_max      = 64;  // blocks averaging <= this many nonzeros per row: one thread per row
     int    vec_lpr          = 0;   // > 0: force this many lanes per row in the vector kernel
     int    gs_multicolor    = 0;   // accept SMOOTHER_GS in the cycle as multicolour GS (OpenMP-FASP semantics)
     int    profile          = 0;   // record CUDA events around every matrix kernel (no graphs)

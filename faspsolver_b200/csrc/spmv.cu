@@ -143,7 +143,7 @@ struct PipeMeta {
     int r0, nrows, k0, n;
 };
 
-template <int MODE, bool PATTERN, int T>
+template <int MODE, bool PATTERN, int T, int UG>
 __global__ void __launch_bounds__(T)
 csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nstages,
                 const int strict, double* partials, unsigned int* ticket)
@@ -224,7 +224,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
                     const int kb   = sia[tid + 1] - k0;
                     const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
                     double    acc  = ModeTraits<MODE>::smoother ? a.b[row] : 0.0;
-                    constexpr int U = 8;
+                    constexpr int U = UG;   // gathers in flight per row thread
                     for (int kk = ka; kk < kb; kk += U) {
                         int    col[U];
                         double xv[U];
@@ -516,7 +516,7 @@ static void launch_vector(const DevCSR& A, const CsrView& v, const CsrArgs& a)
 }
 
 // persistent grid: as many CTAs per SM as the stage rings allow
-template <int MODE, bool PATTERN, int T>
+template <int MODE, bool PATTERN, int T, int UG = 8>
 static void launch_pipe(const DevCSR& A, const CsrView& v, const CsrArgs& a, double* part,
                         unsigned int* tick)
 {
@@ -528,7 +528,7 @@ static void launch_pipe(const DevCSR& A, const CsrView& v, const CsrArgs& a, dou
     const size_t smem = stage * nst;
     static bool  attr_set = false;
     if (!attr_set) {
-        FC_CUDA(cudaFuncSetAttribute(csr_pipe_kernel<MODE, PATTERN, T>,
+        FC_CUDA(cudaFuncSetAttribute(csr_pipe_kernel<MODE, PATTERN, T, UG>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
@@ -538,7 +538,7 @@ static void launch_pipe(const DevCSR& A, const CsrView& v, const CsrArgs& a, dou
     if (per_sm > 2048 / T) per_sm = 2048 / T;
     long long grid = (long long)c.sm_count * per_sm;
     if (grid > A.nblk) grid = A.nblk;
-    FC_LAUNCH((csr_pipe_kernel<MODE, PATTERN, T>), (int)grid, T, smem, v, a, A.nblk, nst,
+    FC_LAUNCH((csr_pipe_kernel<MODE, PATTERN, T, UG>), (int)grid, T, smem, v, a, A.nblk, nst,
               c.opt.strict, part, tick);
 }
 
@@ -565,7 +565,16 @@ static void launch_pattern(const DevCSR& A, const CsrView& v, const CsrArgs& a)
     }
     switch (A.blk_tpb) {
         case 64: launch_pipe<MODE, PATTERN, 64>(A, v, a, part, tick); return;
-        case 128: launch_pipe<MODE, PATTERN, 128>(A, v, a, part, tick); return;
+        case 128:
+            // rows of 6+ entries: 16 gathers in flight per row thread (one round for a 7-point row, two
+            // for the 19-entry rows of the first coarse level instead of three) at 64 registers, still
+            // 8 CTAs per SM; measured +4 % (level 0) and +10 % (level 1) over the 8-deep variant, which
+            // the short rows of the transfer operators keep
+            if (c.opt.gather16_min_avg > 0 && A.rows > 0 && (double)A.nnz >= (double)c.opt.gather16_min_avg * A.rows)
+                launch_pipe<MODE, PATTERN, 128, 16>(A, v, a, part, tick);
+            else
+                launch_pipe<MODE, PATTERN, 128>(A, v, a, part, tick);
+            return;
         default: launch_pipe<MODE, PATTERN, 256>(A, v, a, part, tick); return;
     }
 }
@@ -774,6 +783,7 @@ void csr_upload(DevCSR& d, int rows, int cols, long long nnz, const int* ia, con
     long long cap = (long long)(avg * T + 63) / 64 * 64;
     if (cap < 4 * T) cap = 4 * T;
     int mult = c.opt.pipe_cap_mult;
+    if (avg >= 24.0 && mult == 16) mult = 24;   // measured: 35-entry rows want ~90 rows per block, 19-entry rows ~108
     if (mult < 4) mult = 4;
     if (mult > 32) mult = 32;
     if (cap > (long long)mult * T) cap = (long long)mult * T;

@@ -49,11 +49,17 @@ def test_mxv_matches_reference(gpu, ref, data):
 def test_mxv_short_rows_bit_exact(gpu, ref, data):
     """Rows reduced by a single thread follow the CPU order and rounding exactly."""
     rng = np.random.default_rng(12)
-    for name, A in (("FE", data["FE"]), ("p7_24", PB.poisson7(24)), ("cd7_16", PB.convdiff7(16))):
+    # 27-point rows (22.7 / 24.4 entries on average): still one thread per row, 16 gathers in flight
+    for name, A in (("FE", data["FE"]), ("p7_24", PB.poisson7(24)), ("cd7_16", PB.convdiff7(16)),
+                    ("p27_12", PB.poisson27(12)), ("p27_20", PB.poisson27(20))):
         x = rng.uniform(-1, 1, A.shape[1])
         y = np.empty(A.shape[0])
         assert gpu.fasp_cuda_blas_dcsr_mxv(A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
         assert np.array_equal(y, ref.mxv(A, x)), name
+        y0 = rng.uniform(-1, 1, A.shape[0])
+        y = y0.copy()
+        assert gpu.fasp_cuda_blas_dcsr_aAxpy(-1.0, A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
+        assert np.array_equal(y, ref.aAxpy(-1.0, A, x, y0)), name
 
 
 def test_strict_mode_bit_exact_everywhere(gpu, ref, data):
@@ -145,4 +151,4 @@ def test_wide_row_kernels(gpu, ref, data, lpr):
         assert np.abs(u.a - ur.a).max() <= 1e-12 * max(1.0, np.abs(ur.a).max())
     finally:
         gpu.fasp_cuda_set_option(b"vec_lpr", 0.0)
-        gpu.fasp_cuda_set_option(b"vec_min_avg", 24.0)
+        gpu.fasp_cuda_set_option(b"vec_min_avg", 48.0)
