@@ -1281,6 +1281,7 @@ INT fasp_cuda_smoother_dcsr_gs_multicolor(dvector* u, dCSRmat* A, dvector* b, IN
 } // extern "C"
 
 #include "comm.cuh"
+#include "p2p.cuh"
 extern "C" {
 INT fasp_cuda_comm_unique_id(void* id128)
 {
@@ -1305,6 +1306,7 @@ INT fasp_cuda_comm_finalize(void)
 }
 int fasp_cuda_comm_rank(void) { return comm_rank(); }
 int fasp_cuda_comm_size(void) { return comm_size(); }
+int fasp_cuda_comm_peer_memory(void) { return p2p_active() ? 1 : 0; }
 } // extern "C"
 
 extern "C" INT fasp_cuda_multicolor_host(INT n, const INT* IA, const INT* JA, INT* IC, INT* ICMAP)

@@ -188,7 +188,9 @@ def bench_main(args):
                                    "levels below %d rows replicated" % (args.n, n, A.nnz, world, args.agg_rows),
                        "levels": len(info), "iterations": int(iters), "true_relres": true_rel,
                        "l2_policy": "inputs larger than L2", "setup_s_host": t_setup, "upload_s": t_upload,
-                       "parallelism": "row slabs x%d, NCCL halo send/recv + allreduce" % world},
+                       "parallelism": ("row slabs x%d, ghost push + flag barrier + all-reduce over peer-mapped memory (NVLink)"
+                                       if L.fasp_cuda_comm_peer_memory() else
+                                       "row slabs x%d, NCCL halo send/recv + allreduce") % world},
             "e2e": {"value": float(np.mean(e2e_ms)), "unit": B.UNIT, "h2d_bytes_per_step": int(16 * nloc),
                     "d2h_bytes_per_step": int(8 * nloc)},
             "gpu_launches": launches, "clocks": clocks,

@@ -311,6 +311,9 @@ INT fasp_cuda_comm_init(const void* id128, int rank, int nranks);
 INT fasp_cuda_comm_finalize(void);
 int fasp_cuda_comm_rank(void);
 int fasp_cuda_comm_size(void);
+/* 1 when ghost exchanges and reductions go through peer-mapped memory (CUDA IPC over NVLink),
+ * 0 when they fall back to NCCL send/recv + all-reduce                                       */
+int fasp_cuda_comm_peer_memory(void);
 
 /* Row-partitioned solver: every rank passes the SAME host hierarchy (FASP's deterministic setup run
  * redundantly); levels with >= agg_rows global rows are split into contiguous row slabs (rank r owns
