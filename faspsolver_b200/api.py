@@ -51,6 +51,7 @@ def lib():
         "fasp_cuda_get_option": (C.c_double, [C.c_char_p]),
         "fasp_cuda_blas_dcsr_mxv": (INT, [P(dCSRmat), PREAL, PREAL]),
         "fasp_cuda_blas_dcsr_aAxpy": (INT, [REAL, P(dCSRmat), PREAL, PREAL]),
+        "fasp_cuda_blas_dcsr_vmv": (REAL, [P(dCSRmat), PREAL, PREAL]),
         "fasp_cuda_blas_dcsr_mxv_agg": (INT, [P(dCSRmat), PREAL, PREAL]),
         "fasp_cuda_blas_dcsr_aAxpy_agg": (INT, [REAL, P(dCSRmat), PREAL, PREAL]),
         "fasp_cuda_blas_dbsr_mxv": (INT, [P(dBSRmat), PREAL, PREAL]),
@@ -113,6 +114,7 @@ def lib():
         "fasp_cuda_solver_stat": (C.c_double, [vp, C.c_int]),
         "fasp_cuda_solver_history": (INT, [vp, PREAL, INT]),
         "fasp_cuda_amg_solve": (INT, [P(AMG_data), P(AMG_param)]),
+        "fasp_cuda_solver_amg": (INT, [P(dCSRmat), P(dvector), P(dvector), P(AMG_param)]),
         "fasp_cuda_comm_unique_id": (INT, [vp]),
         "fasp_cuda_comm_init": (INT, [vp, C.c_int, C.c_int]),
         "fasp_cuda_comm_finalize": (INT, []),

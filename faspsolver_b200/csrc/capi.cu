@@ -9,6 +9,7 @@
 #include "krylov.cuh"
 #include "solver.cuh"
 #include <dlfcn.h>
+#include <limits>
 #include <new>
 
 using namespace fc;
@@ -220,6 +221,30 @@ INT fasp_cuda_blas_dcsr_mxv(const dCSRmat* A, const REAL* x, REAL* y)
     API_TRY
     return host_spmv(A, CSR_MXV, 1.0, x, y, false);
     API_CATCH(code__)
+}
+// y^T A x (BlaSpmvCSR.c:839): one fused pass, row sums multiplied by y_i and reduced on the device.
+// Returns NaN (and sets the error string) on failure.
+REAL fasp_cuda_blas_dcsr_vmv(const dCSRmat* A, const REAL* x, const REAL* y)
+{
+    API_TRY
+    ensure_init();
+    check_csr(A);
+    if (A->row == 0) return 0.0;
+    TmpCSR  dA(A);
+    DVec    dx(x, A->col), dy(y, A->row), dw((size_t)A->row);
+    DVec    out((size_t)1);
+    FC_CUDA(cudaMemsetAsync(out.p, 0, sizeof(double), ctx().stream));
+    CsrArgs a;
+    a.mode         = CSR_MXV;
+    a.x            = dx.p;
+    a.y            = dw.p;
+    a.red.dot_with = dy.p;
+    a.red.dot_out  = out.p;
+    csr_launch(dA.m, a);
+    double v = 0.0;
+    out.to_host(&v);
+    return v;
+    API_CATCH(std::numeric_limits<double>::quiet_NaN())
 }
 INT fasp_cuda_blas_dcsr_aAxpy(const REAL alpha, const dCSRmat* A, const REAL* x, REAL* y)
 {
@@ -945,6 +970,47 @@ INT fasp_cuda_amg_solve(AMG_data* mgl, AMG_param* param)
 {
     API_TRY
     return solver_amg_solve(mgl, param);
+    API_CATCH(code__)
+}
+
+// AMG as a solver (SolAMG.c:49-150): host setup, then cycles until ||b - A x|| / ||b|| < param->tol
+INT fasp_cuda_solver_amg(dCSRmat* A, dvector* b, dvector* x, AMG_param* param)
+{
+    API_TRY
+    ensure_init();
+    check_csr(A);
+    if (!b || !x || !param) fail(ERROR_INPUT_PAR, "fasp_cuda_solver_amg: null argument");
+    if (param->cycle_type == AMLI_CYCLE || param->cycle_type == NL_AMLI_CYCLE)
+        fail(ERROR_INPUT_PAR, "AMLI cycles are not on the device path");
+    require_host_fasp();
+    HostFasp& hf  = host_fasp();
+    AMG_data* mgl = hf.amg_data_create(param->max_levels);
+    mgl[0].A      = hf.dcsr_create(A->row, A->col, A->nnz);
+    hf.dcsr_cp(A, &mgl[0].A);
+    mgl[0].b = hf.dvec_create(A->col);
+    mgl[0].x = hf.dvec_create(A->col);
+    memcpy(mgl[0].b.val, b->val, sizeof(REAL) * (size_t)A->col);
+    memcpy(mgl[0].x.val, x->val, sizeof(REAL) * (size_t)A->col);
+    INT st = 0;
+    switch (param->AMG_type) {
+        case SA_AMG: st = hf.setup_sa ? hf.setup_sa(mgl, param) : ERROR_AMG_SETUP; break;
+        case UA_AMG: st = hf.setup_ua ? hf.setup_ua(mgl, param) : ERROR_AMG_SETUP; break;
+        default: st = hf.setup_rs(mgl, param);
+    }
+    if (st < 0) {
+        hf.amg_data_free(mgl, param);
+        fail(ERROR_AMG_SETUP, "host AMG setup failed with status %d", st);
+    }
+    INT iter;
+    try {
+        iter = solver_amg_solve(mgl, param);
+        memcpy(x->val, mgl[0].x.val, sizeof(REAL) * (size_t)A->col);
+    } catch (...) {
+        hf.amg_data_free(mgl, param);
+        throw;
+    }
+    hf.amg_data_free(mgl, param);
+    return iter;
     API_CATCH(code__)
 }
 

@@ -96,6 +96,8 @@ INT fasp_cuda_blas_dcsr_aAxpy(const REAL alpha, const dCSRmat* A, const REAL* x,
 INT fasp_cuda_blas_dcsr_mxv_agg(const dCSRmat* A, const REAL* x, REAL* y);
 /* y = y + alpha*A*x, A entries = 1 replaces fasp_blas_dcsr_aAxpy_agg BlaSpmvCSR.c:727 */
 INT fasp_cuda_blas_dcsr_aAxpy_agg(const REAL alpha, const dCSRmat* A, const REAL* x, REAL* y);
+/* returns y'*A*x (NaN on failure). replaces fasp_blas_dcsr_vmv      BlaSpmvCSR.c:839 */
+REAL fasp_cuda_blas_dcsr_vmv(const dCSRmat* A, const REAL* x, const REAL* y);
 /* y = A*x (block CSR).             replaces fasp_blas_dbsr_mxv      BlaSpmvBSR.c:1055 */
 INT fasp_cuda_blas_dbsr_mxv(const dBSRmat* A, const REAL* x, REAL* y);
 /* y = y + alpha*A*x (block CSR).   replaces fasp_blas_dbsr_aAxpy    BlaSpmvBSR.c:514 */
@@ -225,6 +227,9 @@ INT fasp_cuda_solver_dcsr_pgmres(dCSRmat* A, dvector* b, dvector* x, precond* pc
                                  const REAL tol, const REAL abstol, const INT MaxIt,
                                  const SHORT restart, const SHORT StopType,
                                  const SHORT PrtLvl);
+/* replaces fasp_solver_amg            SolAMG.c:49  (AMG as a solver: host setup, then device cycles until
+ * the relative residual drops below param->tol or param->maxit cycles; AMLI cycles are rejected)           */
+INT fasp_cuda_solver_amg(dCSRmat* A, dvector* b, dvector* x, AMG_param* param);
 /* replaces fasp_solver_dcsr_pvfgmres KryPvfgmres.c:67 (flexible: stores z_j = B p_j, so the
  * preconditioner may change between iterations; stops on ||r|| <= tol * ||b||)            */
 INT fasp_cuda_solver_dcsr_pvfgmres(dCSRmat* A, dvector* b, dvector* x, precond* pc,

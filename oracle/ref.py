@@ -65,6 +65,7 @@ class RefFasp(HostFasp):
             "fasp_param_amg_to_prec": (None, [C.c_void_p, P(AMG_param)]),
             "fasp_dbsr_getdiaginv": (dvector, [P(dBSRmat)]),
             "fasp_solver_amg": (INT, [P(dCSRmat), P(dvector), P(dvector), P(AMG_param)]),
+            "fasp_blas_dcsr_vmv": (REAL, [P(dCSRmat), PREAL, PREAL]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)

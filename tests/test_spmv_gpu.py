@@ -152,3 +152,33 @@ def test_wide_row_kernels(gpu, ref, data, lpr):
     finally:
         gpu.fasp_cuda_set_option(b"vec_lpr", 0.0)
         gpu.fasp_cuda_set_option(b"vec_min_avg", 48.0)
+
+
+# ---- entry points added last in round 1 (kept at the end of the last GPU test module) -------------
+
+def test_vmv_matches_reference(gpu, ref, data):
+    """y'Ax in one fused pass (fasp_blas_dcsr_vmv, BlaSpmvCSR.c:839; used by coarse_scaling)."""
+    rng = np.random.default_rng(31)
+    for name, A in _cases(data):
+        if A.shape[0] != A.shape[1]:
+            continue
+        x, y = rng.uniform(-1, 1, A.shape[1]), rng.uniform(-1, 1, A.shape[0])
+        v = gpu.fasp_cuda_blas_dcsr_vmv(A.ptr(), T.as_preal(x), T.as_preal(y))
+        vr = ref.L.fasp_blas_dcsr_vmv(A.ptr(), T.as_preal(x), T.as_preal(y))
+        bound = float(np.abs(y) @ _bound(A, x))
+        assert abs(v - vr) <= 1e-12 * bound + 1e-300, (name, v, vr)   # reduction order differs
+
+
+def test_solver_amg_drop_in(gpu, ref, data, golden_answers):
+    """fasp_cuda_solver_amg (SolAMG.c:49): setup by the host FASP + device cycles; reg.gcc:412 pins the
+    L1_DIAG recipe on the FE problem at 19 iterations / 8.612004e-11."""
+    g = golden_answers["reg_gcc"]["FE_amg_solver_L1DIAG_tol1e-10"]
+    A, b = data["FE"], data["FE_b"]
+    n = A.shape[0]
+    amg = ref.amg_param(print_level=0, maxit=500, tol=1e-10, smoother=T.SMOOTHER_L1DIAG)
+    vb, vx = T.Vec(b), T.Vec(np.zeros(n))
+    st = gpu.fasp_cuda_solver_amg(A.ptr(), vb.ptr(), vx.ptr(), C.byref(amg))
+    assert st == g["iters"], (st, gpu.fasp_cuda_last_error())
+    relres = np.linalg.norm(b - A.to_scipy() @ vx.a) / np.linalg.norm(b)
+    assert abs(relres - g["relres"]) / g["relres"] < 1e-3, relres
+    assert np.abs(vx.a - data["FE_sol"]).max() < 1e-4
