@@ -64,3 +64,20 @@ def gpu(L):
     if st != 0:
         pytest.fail("libfasp_cuda could not initialise a CUDA device: " + L.fasp_cuda_last_error().decode())
     return L
+
+
+@pytest.fixture(scope="session")
+def c_example_exe(tmp_path_factory):
+    """examples/poisson_amg_cuda.c built with plain gcc against include/fasp_cuda.h, libfasp_cuda and
+    the host FASP (the unmodified reference build under oracle/_ref)."""
+    import subprocess
+    exe = tmp_path_factory.mktemp("c_example") / "poisson_amg_cuda"
+    ref_dir = ROOT / "oracle" / "_ref"
+    if not (ref_dir / "libfasp_seq.so").exists():
+        pytest.skip("oracle/_ref/libfasp_seq.so not built")
+    lib_dir = ROOT / "faspsolver_b200" / "lib"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"),
+                    str(ROOT / "examples" / "poisson_amg_cuda.c"), "-L", str(lib_dir), "-lfasp_cuda",
+                    "-L", str(ref_dir), "-l:libfasp_seq.so", "-lm", "-Wl,-rpath," + str(lib_dir),
+                    "-Wl,-rpath," + str(ref_dir), "-o", str(exe)], check=True)
+    return exe

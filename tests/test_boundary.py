@@ -167,3 +167,13 @@ def test_multicolor_rule_matches_greedy_invariants():
         rows = set(mp[icn[c]:icn[c + 1]].tolist())
         for r in rows:
             assert not (set(S.rows[r]) - {r}) & rows
+
+
+def test_c_application_links_and_fails_loudly_without_device(c_example_exe):
+    """examples/poisson_amg_cuda.c — a FASP application in plain C99 switched to libfasp_cuda — compiles
+    against include/fasp_cuda.h alone, links libfasp_cuda + the host FASP, and without a CUDA device
+    stops with the library's 'no CPU fallback' message (exit status 2) instead of computing on the CPU."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([str(c_example_exe), "8", "0"], capture_output=True, text=True, env=env)
+    assert r.returncode == 2, (r.returncode, r.stdout, r.stderr)
+    assert "no CPU fallback" in r.stderr

@@ -182,3 +182,14 @@ def test_solver_amg_drop_in(gpu, ref, data, golden_answers):
     relres = np.linalg.norm(b - A.to_scipy() @ vx.a) / np.linalg.norm(b)
     assert abs(relres - g["relres"]) / g["relres"] < 1e-3, relres
     assert np.abs(vx.a - data["FE_sol"]).max() < 1e-4
+
+
+def test_c_application_three_usages(gpu, c_example_exe):
+    """examples/poisson_amg_cuda.c on the GPU: drop-in solve, preconditioner plug-in, one hierarchy with
+    several right-hand sides (page-locked application arrays). The program checks the true residual
+    of every solve itself and returns 0 only if all meet the tolerance."""
+    import subprocess
+    for mode in ("0", "1", "2"):
+        r = subprocess.run([str(c_example_exe), "24", mode], capture_output=True, text=True)
+        assert r.returncode == 0, (mode, r.stdout[-1500:], r.stderr[-1500:])
+        assert "iterations, true relative residual" in r.stdout
