@@ -354,6 +354,27 @@ void oracle_precond_amg(omg* g, const double* r, double* z, int maxit)
     for (int i = 0; i < maxit; ++i) oracle_mgcycle(g);
     memcpy(z, g->x[0], n * 8);
 }
+/* AMG as a solver: cycles until ||b - A x|| / ||b|| < tol (fasp_amg_solve, PreMGSolve.c:49-122) */
+int oracle_amg_solve(omg* g, const double* b, double* x, double tol, int MaxIt, double* relres_out)
+{
+    const int    n    = g->A[0].n;
+    const double sumb = o_norm2(n, b);
+    double       relres1 = 1.0;
+    int          iter = 0;
+    memcpy(g->b[0], b, n * 8);
+    memcpy(g->x[0], x, n * 8);
+    if (sumb <= SMALLREAL) memset(g->x[0], 0, n * 8);
+    while ((iter++ < MaxIt) & (sumb > SMALLREAL)) {
+        oracle_mgcycle(g);
+        memcpy(g->w[0], g->b[0], n * 8);
+        oracle_dcsr_aAxpy(-1.0, n, g->A[0].ia, g->A[0].ja, g->A[0].val, g->x[0], g->w[0]);
+        relres1 = o_norm2(n, g->w[0]) / fmax(SMALLREAL, sumb);
+        if (relres1 < tol) break;
+    }
+    memcpy(x, g->x[0], n * 8);
+    if (relres_out) *relres_out = relres1;
+    return iter > MaxIt ? ERROR_SOLVER_MAXIT : iter;
+}
 void oracle_mg_cycle_on(omg* g, const double* b, double* x)
 {
     const int n = g->A[0].n;

@@ -47,6 +47,8 @@ class Oracle:
         L.oracle_pcg.restype = I
         L.oracle_gmres.argtypes = [I, PI, PI, PD, PD, PD, VP, D, D, I, I, I, PD]
         L.oracle_gmres.restype = I
+        L.oracle_amg_solve.argtypes = [VP, PD, PD, D, I, PD]
+        L.oracle_amg_solve.restype = I
         L.oracle_fgmres.argtypes = [I, PI, PI, PD, PD, PD, VP, D, D, I, I, PD]
         L.oracle_fgmres.restype = I
         for f in ("oracle_dcsr_mxv", "oracle_dcsr_aAxpy", "oracle_smoother_jacobi", "oracle_smoother_l1diag",
@@ -116,6 +118,12 @@ class OracleMG:
         rel = C.c_double(0)
         st = self.orc.L.oracle_gmres(A.shape[0], _pi(A.ia), _pi(A.ja), _pd(A.val), _pd(np.ascontiguousarray(b)), _pd(x),
                                      self.h if precond else None, tol, 1e-18, maxit, restart, int(variable), C.byref(rel))
+        return st, x, rel.value
+
+    def amg_solve(self, b, tol=1e-8, maxit=500):
+        x = np.zeros_like(b)
+        rel = C.c_double(0)
+        st = self.orc.L.oracle_amg_solve(self.h, _pd(np.ascontiguousarray(b)), _pd(x), tol, maxit, C.byref(rel))
         return st, x, rel.value
 
     def fgmres(self, A, b, tol=1e-8, maxit=500, restart=30, precond=True):

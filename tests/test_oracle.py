@@ -164,3 +164,26 @@ def test_oracle_flexible_gmres_reproduces_reg_gcc_line(orc, ref, data, golden_an
     assert float("%.6e" % rel) == g["relres"]
     assert np.array_equal(x, vx.a)
     assert np.abs(x - data["FE_sol"]).max() < 1e-4
+
+
+def test_oracle_amg_solver_reproduces_reg_gcc_line(orc, ref, data, golden_answers):
+    """AMG V-cycle with the L1_DIAG smoother as an iterative solver on the FE problem (regression.c:275-289):
+    reg.gcc:412 pins 19 iterations / 8.612004e-11. The restated loop (oracle_amg_solve over the restated
+    cycle; only the coarsest solve is a plain instead of a safeguarded CG) gives the same count and the same
+    printed residual on the reference's own hierarchy."""
+    from oracle.port import OracleMG, hierarchy_from_mgl
+    g = golden_answers["reg_gcc"]["FE_amg_solver_L1DIAG_tol1e-10"]
+    A, b = data["FE"], data["FE_b"]
+    amg = ref.amg_param(print_level=0, maxit=500, tol=1e-10, smoother=T.SMOOTHER_L1DIAG)
+    mgl = ref.amg_setup(A, amg)
+    try:
+        lv = hierarchy_from_mgl(mgl)
+    finally:
+        ref.amg_free(mgl, amg)
+    mg = OracleMG(orc, lv, smoother=amg.smoother, cycle_type=amg.cycle_type, presmooth=amg.presmooth_iter,
+                  postsmooth=amg.postsmooth_iter, ndeg=amg.polynomial_degree, relax=amg.relaxation, tol=amg.tol)
+    st, x, rel = mg.amg_solve(b, tol=1e-10, maxit=500)
+    mg.close()
+    assert st == g["iters"], st
+    assert abs(rel - g["relres"]) / g["relres"] < 1e-5, rel
+    assert np.abs(x - data["FE_sol"]).max() < 1e-4
