@@ -658,3 +658,57 @@ FINISHED:
     free(p), free(z), free(hh), free(r), free(rs), free(c), free(s);
     return iter >= MaxIt ? ERROR_SOLVER_MAXIT : iter;
 }
+
+/* ---- multicolour Gauss-Seidel (the smoother of the reference's OpenMP build) ----
+ * Colouring: dCSRmat_Multicoloring, BlaSparseCSR.c:1687-1770. Rows circulate in a queue; the row at
+ * the front opens a new colour if the queue has wrapped (its index is not larger than the previous
+ * one), is pushed back if a row of the current colour references it, and joins the current colour
+ * otherwise. IC[c] .. IC[c+1] delimit colour c inside ICMAP. Returns the number of colours. */
+int oracle_multicolor(int n, const int* ia, const int* ja, int* IC, int* ICMAP)
+{
+    if (n <= 0) { IC[0] = 0; return 0; }
+    int* q    = malloc(sizeof(int) * (n + 1));
+    int* mark = malloc(sizeof(int) * (n + 1));
+    for (int k = 0; k < n; ++k) q[k] = k, mark[k] = -1;
+    int head = n - 1, tail = n - 1, ncol = 0, filled = 0, last = 0;
+    IC[0] = 0;
+    do {
+        head = (head + 1 == n) ? 0 : head + 1;
+        const int i = q[head];
+        if (i <= last || mark[i] != ncol) {
+            if (i <= last) IC[ncol++] = filled;       /* wrapped: row i starts colour ncol */
+            ICMAP[filled++] = i;
+            for (int k = ia[i]; k < ia[i + 1]; ++k) mark[ja[k]] = ncol;
+        } else {                                      /* coupled to the colour being built */
+            tail = (tail + 1 == n) ? 0 : tail + 1;
+            q[tail] = i;
+        }
+        last = i;
+    } while (tail != head);
+    IC[ncol] = filled;
+    free(q), free(mark);
+    return ncol;
+}
+
+/* L sweeps, colours ascending (order != -1) or descending (order == -1); inside a colour the rows
+ * are independent: u_i = (b_i - sum_{j != i} a_ij u_j) / a_ii, d = the last stored diagonal entry
+ * (fasp_smoother_dcsr_gs_multicolor, BlaSparseCSR.c:2123-2190) */
+void oracle_gs_multicolor(int n, const int* ia, const int* ja, const double* val, const double* b, double* u,
+                          int L, int order, int ncol, const int* IC, const int* ICMAP)
+{
+    (void)n;
+    double d = 0.0; /* as in the reference, d carries over when a row stores no diagonal */
+    while (L--)
+        for (int cc = 0; cc < ncol; ++cc) {
+            const int c = (order == -1) ? ncol - 1 - cc : cc;
+            for (int I = IC[c]; I < IC[c + 1]; ++I) {
+                const int i = ICMAP[I];
+                double    t = b[i];
+                for (int k = ia[i]; k < ia[i + 1]; ++k) {
+                    if (ja[k] != i) t -= val[k] * u[ja[k]];
+                    else d = val[k];
+                }
+                if (fabs(d) > SMALLREAL) u[i] = t / d;
+            }
+        }
+}

@@ -47,6 +47,10 @@ class Oracle:
         L.oracle_pcg.restype = I
         L.oracle_gmres.argtypes = [I, PI, PI, PD, PD, PD, VP, D, D, I, I, I, PD]
         L.oracle_gmres.restype = I
+        L.oracle_multicolor.argtypes = [I, PI, PI, PI, PI]
+        L.oracle_multicolor.restype = I
+        L.oracle_gs_multicolor.argtypes = [I, PI, PI, PD, PD, PD, I, I, I, PI, PI]
+        L.oracle_gs_multicolor.restype = None
         L.oracle_amg_solve.argtypes = [VP, PD, PD, D, I, PD]
         L.oracle_amg_solve.restype = I
         L.oracle_fgmres.argtypes = [I, PI, PI, PD, PD, PD, VP, D, D, I, I, PD]

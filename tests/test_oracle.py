@@ -3,6 +3,8 @@
  (b) the reference library itself (oracle/_ref/libfasp_seq.so) when it has been built here,
 including the reference's own golden log test/out/reg.gcc (via tests/golden/oracle_answers.json)."""
 import ctypes as C
+import json
+import os
 
 import numpy as np
 import pytest
@@ -187,3 +189,70 @@ def test_oracle_amg_solver_reproduces_reg_gcc_line(orc, ref, data, golden_answer
     assert st == g["iters"], st
     assert abs(rel - g["relres"]) / g["relres"] < 1e-5, rel
     assert np.abs(x - data["FE_sol"]).max() < 1e-4
+
+
+_OMP_WORKER = r'''
+import ctypes as C, json, sys
+import numpy as np
+z = np.load(sys.argv[2])
+ia, ja, val = (np.ascontiguousarray(z[k]) for k in ("ia", "ja", "val"))
+b, u0 = np.ascontiguousarray(z["b"]), np.ascontiguousarray(z["u0"])
+n = ia.size - 1
+PI, PD = C.POINTER(C.c_int), C.POINTER(C.c_double)
+class dCSRmat_omp(C.Structure):   # fasp.h:151-180 with MULTI_COLOR_ORDER (the OpenMP build's layout)
+    _fields_ = [("row", C.c_int), ("col", C.c_int), ("nnz", C.c_int), ("IA", PI), ("JA", PI), ("val", PD),
+                ("color", C.c_int), ("IC", PI), ("ICMAP", PI)]
+class dvector(C.Structure):
+    _fields_ = [("row", C.c_int), ("val", PD)]
+L = C.CDLL(sys.argv[1])
+A = dCSRmat_omp(n, n, int(ia[n]), ia.ctypes.data_as(PI), ja.ctypes.data_as(PI), val.ctypes.data_as(PD), 0, None, None)
+rowmax, groups = C.c_int(0), C.c_int(0)
+L.dCSRmat_Multicoloring(C.byref(A), C.byref(rowmax), C.byref(groups))
+ic = [A.IC[k] for k in range(A.color + 1)]
+icmap = [A.ICMAP[k] for k in range(n)]
+out = {"color": A.color, "IC": ic, "ICMAP": icmap, "u": {}}
+for order in (1, -1):
+    u = u0.copy()
+    vu, vb = dvector(n, u.ctypes.data_as(PD)), dvector(n, b.ctypes.data_as(PD))
+    L.fasp_smoother_dcsr_gs_multicolor(C.byref(vu), C.byref(A), C.byref(vb), 2, order)
+    out["u"][str(order)] = u.tolist()
+print(json.dumps(out))
+'''
+
+
+@pytest.mark.parametrize("prob", ["FE", "p7", "p27"])
+def test_multicolour_gs_restatement_equals_openmp_reference(orc, data, tmp_path, prob):
+    """Colouring (dCSRmat_Multicoloring, BlaSparseCSR.c:1687) and two multicolour GS sweeps in both colour
+    orders (fasp_smoother_dcsr_gs_multicolor, :2123) of the unmodified OpenMP reference build, run in a
+    separate process (its dCSRmat layout differs from the sequential build's): the plain-C restatement
+    gives the same colour classes and bit-identical iterates, and so does the host colouring the
+    library ships for its device smoother (fasp_cuda_multicolor_host)."""
+    import subprocess
+    import sys
+    from oracle import ref as R
+    from oracle.port import _pd, _pi
+    from faspsolver_b200 import api
+    if not R.OMP.exists():
+        pytest.skip("oracle/_ref/libfasp_omp.so not built")
+    A = data["FE"] if prob == "FE" else (PB.poisson7(9) if prob == "p7" else PB.poisson27(7))
+    n = A.shape[0]
+    rng = np.random.default_rng(17)
+    b, u0 = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    np.savez(tmp_path / "in.npz", ia=A.ia, ja=A.ja, val=A.val, b=b, u0=u0)
+    script = tmp_path / "omp_worker.py"
+    script.write_text(_OMP_WORKER)
+    r = subprocess.run([sys.executable, str(script), str(R.OMP), str(tmp_path / "in.npz")], capture_output=True,
+                       text=True, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    want = json.loads(r.stdout.strip().splitlines()[-1])
+    ic, icmap = np.zeros(n + 2, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    ncol = orc.L.oracle_multicolor(n, _pi(A.ia), _pi(A.ja), _pi(ic), _pi(icmap))
+    assert ncol == want["color"]
+    assert ic[:ncol + 1].tolist() == want["IC"] and icmap.tolist() == want["ICMAP"]
+    ic2, icmap2 = (C.c_int * (n + 2))(), (C.c_int * n)()
+    assert api.lib().fasp_cuda_multicolor_host(n, _pi(A.ia), _pi(A.ja), ic2, icmap2) == ncol
+    assert list(ic2[:ncol + 1]) == want["IC"] and list(icmap2) == want["ICMAP"]
+    for order in (1, -1):
+        u = u0.copy()
+        orc.L.oracle_gs_multicolor(n, _pi(A.ia), _pi(A.ja), _pd(A.val), _pd(b), _pd(u), 2, order, ncol, _pi(ic), _pi(icmap))
+        assert np.array_equal(u, np.array(want["u"][str(order)])), (prob, order)

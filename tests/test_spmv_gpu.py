@@ -193,3 +193,24 @@ def test_c_application_three_usages(gpu, c_example_exe):
         r = subprocess.run([str(c_example_exe), "24", mode], capture_output=True, text=True)
         assert r.returncode == 0, (mode, r.stdout[-1500:], r.stderr[-1500:])
         assert "iterations, true relative residual" in r.stdout
+
+
+def test_gs_multicolor_drop_in_matches_oracle(gpu, data):
+    """fasp_cuda_smoother_dcsr_gs_multicolor (BlaSparseCSR.c:2123) against the plain-C restatement, which the
+    CPU suite pins bit for bit to the OpenMP reference build (tests/test_oracle.py): two sweeps, both
+    colour orders."""
+    from oracle.port import Oracle, _pd, _pi
+    orc = Oracle()
+    rng = np.random.default_rng(41)
+    for A in (data["FE"], PB.poisson7(12), PB.poisson27(8)):
+        n = A.shape[0]
+        b, u0 = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+        ic, icmap = np.zeros(n + 2, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        ncol = orc.L.oracle_multicolor(n, _pi(A.ia), _pi(A.ja), _pi(ic), _pi(icmap))
+        for order in (1, -1):
+            want = u0.copy()
+            orc.L.oracle_gs_multicolor(n, _pi(A.ia), _pi(A.ja), _pd(A.val), _pd(b), _pd(want), 2, order, ncol,
+                                       _pi(ic), _pi(icmap))
+            vu, vb = T.Vec(u0.copy()), T.Vec(b)
+            assert gpu.fasp_cuda_smoother_dcsr_gs_multicolor(vu.ptr(), A.ptr(), vb.ptr(), 2, order) == 0
+            assert np.abs(vu.a - want).max() <= 1e-13 * max(1.0, np.abs(want).max()), order
