@@ -57,6 +57,7 @@ class RefFasp(HostFasp):
             "fasp_solver_dbsr_pcg": (INT, [P(dBSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT]),
             "fasp_solver_dbsr_pvgmres": (INT, [P(dBSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT, SHORT]),
             "fasp_solver_dcsr_pvfgmres": (INT, [P(dCSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT, SHORT]),
+            "fasp_solver_dbsr_pgmres": (INT, [P(dBSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT, SHORT]),
             "fasp_solver_dbsr_pvfgmres": (INT, [P(dBSRmat), P(dvector), P(dvector), P(precond), REAL, REAL, INT, SHORT, SHORT, SHORT]),
             "fasp_solver_dcsr_krylov_amg": (INT, [P(dCSRmat), P(dvector), P(dvector), P(ITS_param), P(AMG_param)]),
             "fasp_solver_dbsr_krylov_amg": (INT, [P(dBSRmat), P(dvector), P(dvector), P(ITS_param), P(AMG_param)]),

@@ -50,6 +50,13 @@ def main():
         "FE_amg_pcg_default_tol1e-10": {"iters": 6, "relres": 2.728796e-11, "line": 577},
         "FD_amg_pcg_default_tol1e-10": {"iters": 1, "relres": 4.938174e-15, "line": 255},
         "FE_amg_solver_L1DIAG_tol1e-10": {"iters": 19, "relres": 8.612004e-11, "line": 412},
+        # unpreconditioned Krylov methods on the FE problem (regression.c:300-640), CSR and "BSR format" (nb = 1)
+        "FE_cg_unprec_tol1e-12": {"iters": 244, "relres": 9.975280e-13, "line": 451},
+        "FE_gmres_unprec_tol1e-12": {"iters": 937, "relres": 9.895899e-13, "line": 486},
+        "FE_bsr_cg_unprec_tol1e-12": {"iters": 244, "relres": 9.975287e-13, "line": 535, "maxdiff": 9.9928e-08},
+        "FE_bsr_gmres_unprec_tol1e-8": {"iters": 500, "relres": 6.599950e-08, "line": 549, "maxdiff": 2.8813e-06},
+        "FE_bsr_vgmres_unprec_tol1e-8": {"iters": 339, "relres": 9.238968e-09, "line": 556, "maxdiff": 1.8147e-07},
+        "FE_bsr_vfgmres_unprec_tol1e-8": {"iters": 339, "relres": 9.238968e-09, "line": 563, "maxdiff": 1.8147e-07},
         # unpreconditioned variable-restart GMRES and its flexible twin, tol 1e-12, restart 25
         "FE_vgmres_unprec_tol1e-12": {"iters": 493, "relres": 7.667271e-13, "line": 500},
         "FE_vfgmres_unprec_tol1e-12": {"iters": 493, "relres": 7.667271e-13, "line": 514},

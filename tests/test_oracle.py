@@ -256,3 +256,38 @@ def test_multicolour_gs_restatement_equals_openmp_reference(orc, data, tmp_path,
         u = u0.copy()
         orc.L.oracle_gs_multicolor(n, _pi(A.ia), _pi(A.ja), _pd(A.val), _pd(b), _pd(u), 2, order, ncol, _pi(ic), _pi(icmap))
         assert np.array_equal(u, np.array(want["u"][str(order)])), (prob, order)
+
+
+def test_unpreconditioned_krylov_golden_lines(orc, ref, data, golden_answers):
+    """test/out/reg.gcc, FE problem, methods on this path without a preconditioner (regression.c:300-640):
+    the restated CG / GMRES(25) / vGMRES(25) reproduce the iteration counts and the printed residuals to all
+    7 digits, and the compiled reference reproduces the "BSR format" lines (the same matrix as 1x1 blocks:
+    CG 244, GMRES stops at MaxIt = 500, vGMRES / vFGMRES 339) including the logged max-norm error."""
+    g = golden_answers["reg_gcc"]
+    A, b, sol = data["FE"], data["FE_b"], data["FE_sol"]
+    n = A.shape[0]
+    from oracle.port import OracleMG
+    mg = OracleMG.__new__(OracleMG)   # no hierarchy: pc == NULL
+    mg.orc, mg.h = orc, None
+    for key, run in (("FE_cg_unprec_tol1e-12", lambda: mg.pcg(A, b, tol=1e-12, maxit=5000, precond=False)),
+                     ("FE_gmres_unprec_tol1e-12",
+                      lambda: mg.gmres(A, b, tol=1e-12, maxit=5000, restart=25, variable=False, precond=False)),
+                     ("FE_vgmres_unprec_tol1e-12",
+                      lambda: mg.gmres(A, b, tol=1e-12, maxit=5000, restart=25, variable=True, precond=False))):
+        st, x, rel = run()
+        assert st == g[key]["iters"], (key, st)
+        assert float("%.6e" % rel) == g[key]["relres"], (key, rel)
+        assert np.abs(x - sol).max() < 1e-4
+    Ab = T.BSR(n, n, 1, A.ia, A.ja, A.val)
+    S = A.to_scipy()
+    for key, fn, extra in (("FE_bsr_cg_unprec_tol1e-12", ref.L.fasp_solver_dbsr_pcg, (1e-12, 1e-20, 500, 1, 0)),
+                           ("FE_bsr_gmres_unprec_tol1e-8", ref.L.fasp_solver_dbsr_pgmres, (1e-8, 1e-20, 500, 25, 1, 0)),
+                           ("FE_bsr_vgmres_unprec_tol1e-8", ref.L.fasp_solver_dbsr_pvgmres, (1e-8, 1e-20, 500, 25, 1, 0)),
+                           ("FE_bsr_vfgmres_unprec_tol1e-8", ref.L.fasp_solver_dbsr_pvfgmres, (1e-8, 1e-20, 500, 25, 1, 0))):
+        vb, vx = T.Vec(b), T.Vec(np.zeros(n))
+        st = fn(Ab.ptr(), vb.ptr(), vx.ptr(), None, *extra)
+        want = g[key]["iters"]
+        assert st == (want if want < 500 else T.ERROR_SOLVER_MAXIT), (key, st)
+        rel = np.linalg.norm(b - S @ vx.a) / np.linalg.norm(b)
+        assert abs(rel - g[key]["relres"]) / g[key]["relres"] < 1e-5, (key, rel)
+        assert float("%.4e" % np.abs(vx.a - sol).max()) == g[key]["maxdiff"], key
