@@ -25,6 +25,7 @@ struct GmState {
     double r_norm, r_norm_old, absres0, absres, relres, normu, cr, tol, abstol;
     double rr, t2, xx, scale;
     double den_norm, epsilon;   // flexible variant: ||b|| (or ||r0||) and tol * den_norm
+    double b_norm;              // flexible variant: ||b|| as printed by ITS_PUTNORM
     int    iter, maxit, i, stop_type, variable, flexible;
     int    done, converged, silent;
     int    skip_inner, skip_scale, skip_true, skip_copy;
@@ -42,6 +43,7 @@ __global__ void k_gm_init(GmState* st, double* norms, double* habs)
     st->r_norm = sqrt(st->rr);
     if (st->flexible) {   // KryPvfgmres.c:147-167, xx = ||b||^2 here
         const double b_norm = sqrt(st->xx);
+        st->b_norm   = b_norm;
         st->den_norm = (b_norm > 0.0) ? b_norm : st->r_norm;
         st->epsilon  = st->tol * st->den_norm;
         st->absres0 = st->absres = st->r_norm;
@@ -494,7 +496,11 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
             const int           nh = (hs.iter + 1 < hcap) ? hs.iter + 1 : hcap;
             std::vector<double> h2(2 * (size_t)hcap);
             FC_CUDA(cudaMemcpy(h2.data(), norms, sizeof(double) * 2 * hcap, cudaMemcpyDeviceToHost));
-            if (PrtLvl >= PRINT_SOME) {
+            if (PrtLvl >= PRINT_SOME && flexible) {   // ITS_PUTNORM, KryPvfgmres.c:153-156
+                printf("L2 norm of right-hand side = %.10e.\n", hs.b_norm);
+                printf("L2 norm of residual = %.10e.\n", hs.absres0);
+            }
+            if (PrtLvl >= PRINT_SOME && !hs.silent) {   // a solve that stops before the loop prints no table
                 print_itinfo(PrtLvl, StopType, 0, h2[0], hs.absres0, 0.0);
                 for (int i = 1; i < nh; ++i)
                     print_itinfo(PrtLvl, StopType, i, h2[i], h2[hcap + i], h2[i] / h2[i - 1]);
