@@ -263,7 +263,7 @@ def run_ours(args):
     alg_per_launch = float(np.mean([by for *_, by in lvl0])) if lvl0 else None
     roofline = {"bound": "hbm", "kernel": "csr_pipe_kernel on the level-0 matrix (SpMV / residual / L1-Jacobi sweep), "
                                           "CUDA events around every launch of one solve",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0, "traffic": traffic,
                 "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_per_launch,
                 "launch_ms": l0_ms / len(lvl0) if lvl0 else None,
                 "peak_source": peak_src, "share_of_matrix_kernel_time": l0_ms / tot_ms if tot_ms else None,

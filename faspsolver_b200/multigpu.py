@@ -162,7 +162,7 @@ def bench_main(args):
         peak, src = B.peaks()
         comm_ms = sum(r[3] for r in recs if r[0] >= 400)
         roofline = {"bound": "hbm", "kernel": "csr_pipe_kernel on rank 0's level-0 slab (%d rows, %d nnz)" % (nloc, top),
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0, "traffic": None,
                     "peak_source": src, "launch_ms": t_ms / len(l0),
                     "comm_ms_per_solve_profiled": comm_ms, "comm_ops_per_solve": len([r for r in recs if r[0] >= 400])}
     # true residual of the assembled solution (rank 0)
