@@ -251,15 +251,20 @@ def run_ours(args):
     ach = float(sum(by for *_, by in lvl0) / l0_ms * 1e-6) if l0_ms > 0 else 0.0
     # DRAM traffic per launch of the same kernel from the committed ncu --set full capture
     traffic, traffic_src = None, None
-    tf = ROOT / "profiles" / "r01_ncu_traffic.json"
-    if tf.exists() and args.n == 256:
-        tj = json.loads(tf.read_text())
+    tfs = sorted((ROOT / "profiles").glob("r*_ncu_traffic.json"))
+    if tfs and args.n == 256:
+        tj = json.loads(tfs[-1].read_text())
         ks = tj["kernels"]
         per = {"resid": ks.get("resid"), "l1": ks.get("l1"), "mxv": ks.get("mxv") or ks.get("resid")}
         num = sum(per[kind_names[k]]["traffic"] * len(v) for k, v in by_kind.items() if per.get(kind_names.get(k)))
         den = sum(len(v) for k, v in by_kind.items() if per.get(kind_names.get(k)))
         traffic = num / den if den else None
-        traffic_src = tj["source"]
+        traffic_src = tfs[-1].name + ": " + tj["source"]
+        # the capture belongs to one version of the kernel source: say so when the kernel has changed since
+        import hashlib
+        sha = hashlib.sha256((ROOT / "faspsolver_b200" / "csrc" / "spmv.cu").read_bytes()).hexdigest()[:16]
+        if tj.get("spmv_cu_sha16") and tj["spmv_cu_sha16"] != sha:
+            traffic_src += " [captured before the last change of spmv.cu]"
     alg_per_launch = float(np.mean([by for *_, by in lvl0])) if lvl0 else None
     roofline = {"bound": "hbm", "kernel": "csr_pipe_kernel on the level-0 matrix (SpMV / residual / L1-Jacobi sweep), "
                                           "CUDA events around every launch of one solve",
@@ -299,7 +304,48 @@ def run_ours(args):
     }
     solver.close()
     hf.amg_free(mgl, amg)
+    if args.extras and args.n == 256:
+        out["extra"] = run_extras(args, local)
     return out
+
+
+def run_extras(args, local):
+    """BASELINE configs[3] (conv-diff 256^3 GMRES(30) + polynomial smoother) and configs[4] (BSR 272^3) in two
+    separate processes after the headline measurement is complete: their host setups (single-threaded FASP
+    code, ~100 s and ~20 s) overlap, their GPU phases are serialised by a lock file. A config that fails or runs
+    out of its time budget is reported as unavailable; the headline line is never at risk."""
+    import tempfile
+    script = str(ROOT / "scripts" / "bench_configs.py")
+    lock = tempfile.NamedTemporaryFile(prefix="fasp_bench_gpu_", suffix=".lock", delete=False).name
+    env = dict(os.environ, LOCAL_RANK=str(local))
+    jobs = {}
+    for key, cfg, n, budget in (("config4", 4, args.c4_n, 420), ("config5", 5, args.c5_n, 420)):
+        cmd = [sys.executable, script, "--config", str(cfg), "--n", str(n), "--lock", lock]
+        for kv in args.opt:
+            cmd += ["--opt", kv]
+        jobs[key] = (subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True),
+                     time.time(), budget)
+    res = {}
+    for key, (proc, t0, budget) in jobs.items():
+        try:
+            so, se = proc.communicate(timeout=max(1.0, budget - (time.time() - t0)))
+        except subprocess.TimeoutExpired:
+            proc.kill()
+            so, se = proc.communicate()
+            res[key] = {"unavailable": "did not finish within %d s" % budget}
+            continue
+        sys.stderr.write(se[-3000:])
+        line = [ln for ln in so.splitlines() if ln.startswith("{")]
+        if proc.returncode != 0 or not line:
+            res[key] = {"unavailable": "rc=%d: %s" % (proc.returncode, se.strip().splitlines()[-1][:300] if se.strip() else "")}
+        else:
+            res[key] = json.loads(line[-1])
+            res[key]["wall_s"] = round(time.time() - t0, 1)
+    try:
+        os.unlink(lock)
+    except OSError:
+        pass
+    return res
 
 
 def cpu_baseline_sample(hf, A, b, mgl, amg, it, full_iters, args):
@@ -346,9 +392,15 @@ def run_reference(args):
         return {"impl": "reference", "unavailable": "oracle/_ref/fasp_ref_bench not built (oracle/build_ref.sh)"}
     env = dict(os.environ)
     ncores = os.cpu_count() or 1
-    env.setdefault("OMP_NUM_THREADS", str(ncores))
-    env.setdefault("OMP_PROC_BIND", "true")
-    env.setdefault("OMP_PLACES", "cores")
+    try:
+        ncores = len(os.sched_getaffinity(0)) or ncores
+    except Exception:
+        pass
+    # assignment, not setdefault: torchrun exports OMP_NUM_THREADS=1 to its workers, which would time the
+    # reference on one thread. Rank 0 runs alone (the other ranks exit), so it takes every host core.
+    env["OMP_NUM_THREADS"] = str(int(os.environ.get("FASP_REF_THREADS", ncores)))
+    env["OMP_PROC_BIND"] = "true"
+    env["OMP_PLACES"] = "cores"
     cmd = [str(exe), str(args.n), str(args.steps), str(args.warmup), str(args.ref_sample_iters)]
     log("[bench] reference arm:", " ".join(cmd), "OMP_NUM_THREADS=%s" % env["OMP_NUM_THREADS"])
     r = subprocess.run(cmd, env=env, capture_output=True, text=True)
@@ -358,14 +410,15 @@ def run_reference(args):
         return {"impl": "reference", "unavailable": "fasp_ref_bench failed rc=%d" % r.returncode}
     d = json.loads(line[-1])
     n = args.n ** 3
-    val = d["ms_per_solve_est"]
+    val = d["ms_per_solve"]
     return {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": val, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[1]: 3D 7-point Poisson %d^3 (%d rows), rhs=1, AMG-PCG tol 1e-8, classical RS, "
                                "OpenMP FASP (runs multicolour GS regardless of the requested smoother)" % (args.n, n),
-                   "levels": d.get("levels"), "iterations": d.get("iterations"), "setup_s": d.get("setup_s")},
+                   "levels": d.get("levels"), "iterations": d.get("iterations"), "setup_s": d.get("setup_s"),
+                   "extrapolated": d.get("extrapolated"), "ms_first_solve": d.get("ms_first_solve")},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": d.get("threads"), "kind": "reference",
                          "sample": d.get("sample")},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -381,7 +434,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("FASP_BENCH_N", "256")))
     ap.add_argument("--cpu-sample-iters", type=int, default=3)
-    ap.add_argument("--ref-sample-iters", type=int, default=2)
+    ap.add_argument("--ref-sample-iters", type=int, default=0,
+                    help="reference arm: 0 = every step is a full solve (default); k > 0 = k-iteration samples, scaled")
+    ap.add_argument("--extras", type=int, default=int(os.environ.get("FASP_BENCH_EXTRAS", "1")),
+                    help="N = 1: also measure BASELINE configs 4 and 5 (separate processes, bounded) -> extra.config4/5")
+    ap.add_argument("--c4-n", type=int, default=256)
+    ap.add_argument("--c5-n", type=int, default=272)
     ap.add_argument("--opt", action="append", default=[], help="libfasp_cuda option key=value")
     ap.add_argument("--agg-rows", type=int, default=8000,
                     help="multi-GPU: levels with fewer global rows are replicated instead of partitioned")

@@ -56,6 +56,15 @@ def lib():
         "fasp_cuda_blas_dcsr_aAxpy_agg": (INT, [REAL, P(dCSRmat), PREAL, PREAL]),
         "fasp_cuda_blas_dbsr_mxv": (INT, [P(dBSRmat), PREAL, PREAL]),
         "fasp_cuda_blas_dbsr_aAxpy": (INT, [REAL, P(dBSRmat), PREAL, PREAL]),
+        "fasp_cuda_blas_darray_ax": (INT, [INT, REAL, PREAL]),
+        "fasp_cuda_blas_darray_axpy": (INT, [INT, REAL, PREAL, PREAL]),
+        "fasp_cuda_blas_darray_axpby": (INT, [INT, REAL, PREAL, REAL, PREAL]),
+        "fasp_cuda_blas_darray_dotprod": (REAL, [INT, PREAL, PREAL]),
+        "fasp_cuda_blas_darray_norm2": (REAL, [INT, PREAL]),
+        "fasp_cuda_blas_darray_norm1": (REAL, [INT, PREAL]),
+        "fasp_cuda_blas_darray_norminf": (REAL, [INT, PREAL]),
+        "fasp_cuda_solver_matfree_init": (INT, [INT, P(T.mxv_matfree), vp]),
+        "fasp_cuda_dense_inverse": (INT, [INT, PREAL, PREAL]),
         "fasp_cuda_blas_mxv_csr": (None, [vp, PREAL, PREAL]),
         "fasp_cuda_blas_mxv_bsr": (None, [vp, PREAL, PREAL]),
         "fasp_cuda_smoother_dcsr_jacobi": (INT, [P(dvector), INT, INT, INT, P(dCSRmat), P(dvector), INT, REAL]),
@@ -129,7 +138,7 @@ def lib():
     for name, (res, args) in sig.items():
         try:
             f = getattr(L, name)
-        except AttributeError:  # tests/test_exports.py fails on any such symbol
+        except AttributeError:  # tests/test_boundary.py::test_library_exports_every_declared_symbol fails on it
             missing.append(name)
             continue
         f.restype = res

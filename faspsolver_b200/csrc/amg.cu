@@ -103,6 +103,25 @@ void amg_level_smoother_data(Amg& h, Level& L, const dCSRmat* hostA)
     }
 }
 
+// Coarsest level: dense inverse (the default up to coarse_dense_max rows) or, when the level is too large,
+// option coarse_dense = 0, or the factorisation meets a vanishing pivot, CG in one cooperative kernel to the
+// reference's coarse tolerance param->tol * 1e-4 (PreMGCycle.c:56, PreMGUtil.inl:37-58).
+void amg_setup_coarse(Amg& h)
+{
+    Level& C = h.lv[h.nl - 1];
+    h.coarse_iterative = true;
+    if (ctx().opt.coarse_dense && C.n <= ctx().opt.coarse_dense_max) {
+        if (dense_invert_csr(h.coarse, C.A)) {
+            h.coarse_iterative = false;
+            h.bytes += sizeof(double) * (size_t)C.n * C.n;
+        }
+    }
+    if (h.coarse_iterative) {
+        coarse_cg_setup(h.coarse_cg, C.A, h.tol * 1e-4);
+        h.bytes += sizeof(double) * 3 * (size_t)C.n;
+    }
+}
+
 Amg* amg_upload(AMG_data* mgl, AMG_param* param)
 {
     ensure_init();
@@ -144,17 +163,7 @@ Amg* amg_upload(AMG_data* mgl, AMG_param* param)
         }
         h->scal = dalloc<double>(4);
         FC_CUDA(cudaMemsetAsync(h->scal, 0, 4 * sizeof(double), ctx().stream));
-        // coarsest level
-        Level& C = h->lv[nl - 1];
-        if (ctx().opt.coarse_dense && C.n <= ctx().opt.coarse_dense_max) {
-            dense_invert_csr(h->coarse, C.A);
-            h->bytes += sizeof(double) * (size_t)C.n * C.n;
-        } else {
-            fail(ERROR_AMG_SETUP,
-                 "coarsest level has %d rows > coarse_dense_max = %d: raise the option or let the "
-                 "host setup coarsen further",
-                 C.n, ctx().opt.coarse_dense_max);
-        }
+        amg_setup_coarse(*h);
         FC_CUDA(cudaStreamSynchronize(ctx().stream));
     } catch (...) {
         amg_free(h);
@@ -186,6 +195,7 @@ void amg_free(Amg* h)
         halo_free(L.hR);
     }
     dense_free(h->coarse);
+    coarse_cg_free(h->coarse_cg);
     dfree(h->scal);
     delete h;
 }
@@ -322,7 +332,8 @@ void coarse_solve(CycleState& s, bool last)
     Amg& h      = s.h;
     const int l = h.nl - 1;
     double* out = last ? s.x_out : s.cur[l];
-    dense_apply(h.coarse, s.rhs(l), out, s.done);
+    if (h.coarse_iterative) coarse_cg_apply(h.coarse_cg, h.lv[l].A, s.rhs(l), out, s.done);
+    else dense_apply(h.coarse, s.rhs(l), out, s.done);
     s.cur[l]   = out;
     s.xzero[l] = false;
 }
@@ -375,7 +386,7 @@ void run_cycle(CycleState& s)
             if (gather_next) r.y += L.gdispls[comm_rank()];
             csr_launch(L.R, r);
             if (gather_next)
-                comm_allgatherv(r.y, L.gcounts[comm_rank()], h.lv[l + 1].b, L.gcounts, L.gdispls);
+                comm_allgatherv(r.y, L.gcounts[comm_rank()], h.lv[l + 1].b, L.gcounts, L.gdispls, s.done);
             ++l;
             s.cur[l]   = h.lv[l].xa;
             s.xzero[l] = true;   // fasp_dvec_set(..., 0.0) (:151) is folded into the next writer
@@ -395,7 +406,7 @@ void run_cycle(CycleState& s)
             p.done = s.done;
             if (h.coarse_scaling == ON) {   // (:210-216)
                 vec_dot(s.cur[l + 1], Lc.b, Lc.n, h.scal + 1, s.done);
-                if (Lc.dist) comm_allreduce(h.scal + 1, 1);
+                if (Lc.dist) comm_allreduce(h.scal + 1, 1, 0, s.done);
                 CsrArgs v;
                 v.mode         = CSR_MXV;
                 v.x            = s.cur[l + 1];

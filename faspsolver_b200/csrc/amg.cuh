@@ -10,11 +10,26 @@ struct DenseInv {
     int     n    = 0;
     double* ainv = nullptr;   // n x n row-major
 };
-void dense_invert_csr(DenseInv& D, const DevCSR& A);       // Gauss-Jordan, partial pivoting
-void dense_invert_host(DenseInv& D, int n, const std::vector<double>& a_rowmajor);
-void dense_invert_bsr(DenseInv& D, const DevBSR& A);          // expanded to (ROW nb)^2
+// Blocked Gauss-Jordan with partial pivoting (dense.cu). Return false, with D left empty, when the matrix is
+// numerically singular (a pivot below 1e-14 of the largest entry): the caller falls back to the iterative
+// coarse solve or reports ERROR_AMG_SETUP instead of applying an inf/NaN inverse.
+bool dense_invert_csr(DenseInv& D, const DevCSR& A);
+bool dense_invert_host(DenseInv& D, int n, const std::vector<double>& a_rowmajor);
+bool dense_invert_bsr(DenseInv& D, const DevBSR& A);          // expanded to (ROW nb)^2
 void dense_apply(const DenseInv& D, const double* b, double* x, const int* done);
 void dense_free(DenseInv& D);
+
+// iterative coarsest-level solve (coarse.cu): CG to tol in one persistent cooperative kernel
+struct CoarseCG {
+    int     n = 0, grid = 0, maxit = 0;
+    double  tol  = 1e-10;
+    double* work = nullptr;   // p, r, t (n each) + per-CTA partials
+    int*    iters = nullptr;  // device: iterations of the last solve
+};
+void coarse_cg_setup(CoarseCG& C, const DevCSR& A, double tol);
+void coarse_cg_apply(const CoarseCG& C, const DevCSR& A, const double* b, double* x, const int* done);
+void coarse_cg_free(CoarseCG& C);
+int  coarse_cg_last_iters(const CoarseCG& C);
 
 struct Level {
     DevCSR  A, P, R;          // P: level l <- l+1 ; R: level l+1 <- l   (R = P^T stored explicitly)
@@ -50,6 +65,8 @@ struct Amg {
     double relax = 1.0, tol = 1e-6;
     int    maxit = 1;             // cycles per preconditioner application (PreCSR.c:432)
     DenseInv coarse;
+    CoarseCG coarse_cg;           // used instead of `coarse` when the dense inverse is unavailable
+    bool     coarse_iterative = false;
     double*  scal = nullptr;      // device scalars: [0] alpha (coarse scaling), [1],[2] dots
     size_t   bytes = 0;
     long long kernels_per_cycle = 0;
@@ -62,6 +79,7 @@ void gs_multicolor_sweeps(const DevCSR& A, const int* color_rows, const std::vec
 
 // Build from a host hierarchy produced by FASP's setup (fasp.h:804-888).
 Amg* amg_upload(AMG_data* mgl, AMG_param* param);
+void amg_setup_coarse(Amg& h);   // dense inverse of the coarsest level, or the iterative fallback
 void amg_free(Amg* h);
 void amg_set_params(Amg& h, const AMG_param* param);
 void amg_level_smoother_data(Amg& h, Level& L, const dCSRmat* hostA);
@@ -86,6 +104,7 @@ struct BLevel {
     double* xb = nullptr;
     double* w = nullptr;
     double* diaginv = nullptr;   // ROW * nb*nb inverted diagonal blocks
+    double *peh = nullptr, *aeh = nullptr;   // coarse_scaling: P e and A P e (PreMGCycle.c:467-471)
 };
 struct BAmg {
     std::vector<BLevel> lv;
@@ -95,6 +114,7 @@ struct BAmg {
     double relax = 1.0, tol = 1e-6;
     int    maxit = 1;
     DenseInv coarse;
+    double*  scal = nullptr;   // device scalars of the coarse-grid scaling
     size_t bytes = 0;
 };
 BAmg* bamg_upload(AMG_data_bsr* mgl, AMG_param* param);

@@ -24,7 +24,6 @@ BAmg* bamg_upload(AMG_data_bsr* mgl, AMG_param* param)
              (int)param->smoother);
     if (param->cycle_type != V_CYCLE && param->cycle_type != W_CYCLE)
         fail(ERROR_INPUT_PAR, "BSR cycle: cycle_type %d is not on the device path", (int)param->cycle_type);
-    if (param->coarse_scaling == ON) fail(ERROR_INPUT_PAR, "BSR cycle: coarse_scaling is not on the device path");
 
     BAmg* h = new BAmg();
     try {
@@ -32,6 +31,9 @@ BAmg* bamg_upload(AMG_data_bsr* mgl, AMG_param* param)
         h->smoother = param->smoother, h->cycle_type = param->cycle_type;
         h->presmooth = param->presmooth_iter, h->postsmooth = param->presmooth_iter;
         h->relax = param->relaxation, h->tol = param->tol, h->maxit = param->maxit;
+        h->coarse_scaling = param->coarse_scaling;
+        h->scal = dalloc<double>(4);
+        FC_CUDA(cudaMemsetAsync(h->scal, 0, 4 * sizeof(double), ctx().stream));
         h->lv.resize(nl);
         for (int l = 0; l < nl; ++l) {
             BLevel&        L = h->lv[l];
@@ -41,8 +43,14 @@ BAmg* bamg_upload(AMG_data_bsr* mgl, AMG_param* param)
             if (l < nl - 1) {
                 const dBSRmat& P = mgl[l].P;
                 const dBSRmat& R = mgl[l].R;
-                bsr_upload(L.P, P.ROW, P.COL, P.NNZ, P.nb, P.IA, P.JA, P.val);
-                bsr_upload(L.R, R.ROW, R.COL, R.NNZ, R.nb, R.IA, R.JA, R.val);
+                // UA-AMG: identity transfer blocks -> pattern-only gather / segmented sum (4 B per block)
+                bsr_upload(L.P, P.ROW, P.COL, P.NNZ, P.nb, P.IA, P.JA, P.val, true);
+                bsr_upload(L.R, R.ROW, R.COL, R.NNZ, R.nb, R.IA, R.JA, R.val, true);
+                if (h->coarse_scaling == ON) {
+                    L.peh = dalloc<double>((size_t)A.ROW * A.nb);
+                    L.aeh = dalloc<double>((size_t)A.ROW * A.nb);
+                    h->bytes += 2 * sizeof(double) * (size_t)A.ROW * A.nb;
+                }
                 const size_t nd = (size_t)A.ROW * A.nb * A.nb;
                 if (mgl[l].diaginv.val == nullptr || (size_t)mgl[l].diaginv.row < nd)
                     fail(ERROR_DATA_STRUCTURE, "level %d has no diaginv (host setup incomplete)", l);
@@ -61,7 +69,8 @@ BAmg* bamg_upload(AMG_data_bsr* mgl, AMG_param* param)
         if (C.n > ctx().opt.coarse_dense_max)
             fail(ERROR_AMG_SETUP, "coarsest BSR level has %d unknowns > coarse_dense_max = %d", C.n,
                  ctx().opt.coarse_dense_max);
-        dense_invert_bsr(h->coarse, C.A);
+        if (!dense_invert_bsr(h->coarse, C.A))
+            fail(ERROR_AMG_SETUP, "coarsest BSR level is numerically singular (pivot below 1e-14 of the largest entry)");
         h->bytes += sizeof(double) * (size_t)C.n * C.n;
         FC_CUDA(cudaStreamSynchronize(ctx().stream));
     } catch (...) {
@@ -83,8 +92,11 @@ void bamg_free(BAmg* h)
         dfree(L.xb);
         dfree(L.w);
         dfree(L.diaginv);
+        dfree(L.peh);
+        dfree(L.aeh);
     }
     dense_free(h->coarse);
+    dfree(h->scal);
     delete h;
 }
 
@@ -110,11 +122,25 @@ void bsmooth(BCycle& s, int l, int nsweeps, bool last)
     for (int sw = 0; sw < nsweeps; ++sw) {
         const bool final_sweep = last && sw == nsweeps - 1;
         double*    out         = final_sweep ? s.x_out : s.other(l);
+        BsrArgs a;
+        if (s.xzero[l] && ctx().opt.zero_guess) {
+            // first sweep from x = 0: b - sum A_IJ 0 == b exactly, so u_I = Dinv_I b_I without a pass over A
+            a.mode    = BSR_DINV;
+            a.b       = s.rhs(l);
+            a.y       = out;
+            a.diaginv = L.diaginv;
+            a.red     = final_sweep ? s.red : Reduce();
+            a.done    = s.done;
+            bsr_launch(L.A, a);
+            if (final_sweep) s.red_done = true;
+            s.cur[l]   = out;
+            s.xzero[l] = false;
+            continue;
+        }
         if (s.xzero[l]) {
             vec_set(s.cur[l], 0.0, L.n, s.done);
             s.xzero[l] = false;
         }
-        BsrArgs a;
         a.mode    = BSR_JACOBI;
         a.x       = s.cur[l];
         a.b       = s.rhs(l);
@@ -169,13 +195,34 @@ void brun_cycle(BCycle& s)
         while (l > 0) {   // BackwardSweep (:462-560)
             --l;
             BLevel& L = h.lv[l];
-            BsrArgs p;
-            p.mode  = BSR_AXPY;
-            p.alpha = 1.0;
-            p.x     = s.cur[l + 1];
-            p.y     = s.cur[l];
-            p.done  = s.done;
-            bsr_launch(L.P, p);
+            if (h.coarse_scaling == ON) {
+                // alpha = min((A P e, w) / (A P e, A P e), 1) ; x += alpha P e   (PreMGCycle.c:465-480)
+                BsrArgs pe;
+                pe.mode = BSR_MXV;
+                pe.x    = s.cur[l + 1];
+                pe.y    = L.peh;
+                pe.done = s.done;
+                bsr_launch(L.P, pe);
+                BsrArgs ae;
+                ae.mode         = BSR_MXV;
+                ae.x            = L.peh;
+                ae.y            = L.aeh;
+                ae.red.dot_with = L.w;
+                ae.red.dot_out  = h.scal + 1;
+                ae.red.nrm2_out = h.scal + 2;
+                ae.done         = s.done;
+                bsr_launch(L.A, ae);
+                scaling_alpha(h.scal, s.done);
+                vec_axpy_dev(h.scal, L.peh, s.cur[l], L.n, s.done);
+            } else {
+                BsrArgs p;
+                p.mode  = BSR_AXPY;
+                p.alpha = 1.0;
+                p.x     = s.cur[l + 1];
+                p.y     = s.cur[l];
+                p.done  = s.done;
+                bsr_launch(L.P, p);
+            }
             bsmooth(s, l, h.postsmooth, l == 0);
             if (nu_l[l] < h.cycle_type) break;
             nu_l[l] = 0;

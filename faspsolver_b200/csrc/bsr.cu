@@ -18,7 +18,6 @@
 
 namespace fc {
 
-constexpr int B_RB         = 32;   // block rows per CTA
 constexpr int B_MAX_STAGES = 4;
 
 struct BsrView {
@@ -34,7 +33,8 @@ struct BMeta {
     int r0, nrows, k0, n;
 };
 
-template <int MODE, int NB>
+// B_RB block rows per CTA (NB threads each), U blocks of a row in flight per thread
+template <int MODE, int NB, int B_RB, int U>
 __global__ void __launch_bounds__(B_RB* NB)
 bsr_pipe_kernel(const BsrView A, const BsrArgs a, const int nblk, const int nstages,
                 double* partials, unsigned int* ticket)
@@ -127,7 +127,6 @@ bsr_pipe_kernel(const BsrView A, const BsrArgs a, const int nblk, const int nsta
                 acc = (a.alpha == 1.0) ? y0 : __dmul_rn(1.0 / a.alpha, y0);   // fasp_blas_darray_ax
             } else acc = a.b[row];
 
-            constexpr int U = (NB <= 4) ? 4 : 2;
             for (int kk = ka; kk < kb; kk += U) {
                 int    col[U];
                 double xv[U][NB];
@@ -208,20 +207,109 @@ bsr_pipe_kernel(const BsrView A, const BsrArgs a, const int nblk, const int nsta
     }
 }
 
-template <int MODE, int NB>
-static void launch_nb(const DevBSR& A, const BsrView& v, const BsrArgs& a)
+// ------------------------------------------------------------------------------------
+// identity-block operators (UA-AMG P / R): y_I (+)= sum_{k in row I} x_{ja[k]} per scalar component.
+// The CPU code multiplies by the stored identity blocks (fasp_blas_dbsr_mxv/aAxpy, 76 B per block);
+// 1*x_i + 0*x_j + 0*x_k == x_i, so summing the gathered entries in k order is bit-identical.
+// ------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+bsr_ident_kernel(const int ROW, const int nb, const int* __restrict__ ia, const int* __restrict__ ja,
+                 const BsrArgs a, double* partials, unsigned int* ticket)
+{
+    if (a.done != nullptr && *a.done != 0) return;
+    const long long n  = (long long)ROW * nb;
+    double     red_dot = 0.0, red_n2 = 0.0;
+    const bool want_dot = a.red.dot_out != nullptr, want_n2 = a.red.nrm2_out != nullptr;
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < n; t += (long long)gridDim.x * 256) {
+        const int I = (int)(t / nb), i = (int)(t - (long long)I * nb);
+        double acc;
+        if (MODE == BSR_MXV) acc = 0.0;
+        else if (MODE == BSR_AXPY) acc = (a.alpha == 1.0) ? a.y[t] : __dmul_rn(1.0 / a.alpha, a.y[t]);
+        else acc = a.b[t];
+        for (int k = ia[I]; k < ia[I + 1]; ++k) {
+            const double xv = __ldg(a.x + (size_t)ja[k] * nb + i);
+            acc = (MODE == BSR_RESID) ? __dsub_rn(acc, xv) : __dadd_rn(acc, xv);
+        }
+        if (MODE == BSR_AXPY && a.alpha != 1.0) acc = __dmul_rn(a.alpha, acc);
+        a.y[t] = acc;
+        if (want_dot) red_dot += acc * a.red.dot_with[t];
+        if (want_n2) red_n2 += acc * acc;
+    }
+    if (want_dot || want_n2) {
+        double v[2] = {red_dot, red_n2};
+        grid_reduce<2, 0>(v, partials, ticket, [&](const double* t) {
+            if (want_dot) *a.red.dot_out = t[0];
+            if (want_n2) *a.red.nrm2_out = t[1];
+        });
+    }
+}
+
+// y_I = Dinv_I b_I (fasp_blas_smat_mxv, BlaSmallMat.c:238): thread per scalar row
+__global__ void __launch_bounds__(256)
+bsr_dinv_kernel(const int ROW, const int nb, const BsrArgs a, double* partials, unsigned int* ticket)
+{
+    if (a.done != nullptr && *a.done != 0) return;
+    const long long n  = (long long)ROW * nb;
+    double     red_dot = 0.0, red_n2 = 0.0;
+    const bool want_dot = a.red.dot_out != nullptr, want_n2 = a.red.nrm2_out != nullptr;
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < n; t += (long long)gridDim.x * 256) {
+        const int     I = (int)(t / nb), i = (int)(t - (long long)I * nb);
+        const double* D = a.diaginv + ((size_t)I * nb + i) * nb;
+        const double* bb = a.b + (size_t)I * nb;
+        double        e;
+        if (nb <= 7) {   // the unrolled nc2/nc3/nc5/nc7 (and 4, 6) expressions start from the first product
+            e = __dmul_rn(D[0], bb[0]);
+            for (int j = 1; j < nb; ++j) e = __dadd_rn(e, __dmul_rn(D[j], bb[j]));
+        } else {
+            e = 0.0;
+            for (int j = 0; j < nb; ++j) e = __dadd_rn(e, __dmul_rn(D[j], bb[j]));
+        }
+        a.y[t] = e;
+        if (want_dot) red_dot += e * a.red.dot_with[t];
+        if (want_n2) red_n2 += e * e;
+    }
+    if (want_dot || want_n2) {
+        double v[2] = {red_dot, red_n2};
+        grid_reduce<2, 0>(v, partials, ticket, [&](const double* t) {
+            if (want_dot) *a.red.dot_out = t[0];
+            if (want_n2) *a.red.nrm2_out = t[1];
+        });
+    }
+}
+
+static int flat_grid(long long n)
+{
+    long long g = (n + 1023) / 1024, cap = (long long)ctx().sm_count * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+template <int MODE>
+static void launch_ident(const DevBSR& A, const BsrArgs& a)
+{
+    const int g = flat_grid((long long)A.ROW * A.nb);
+    FC_LAUNCH((bsr_ident_kernel<MODE>), g, 256, 0, A.ROW, A.nb, A.ia, A.ja, a, red_partials(g), red_ticket());
+}
+
+template <int MODE, int NB, int B_RB, int U>
+static void launch_var(const DevBSR& A, const BsrView& v, const BsrArgs& a)
 {
     Ctx&         c    = ctx();
     const size_t vald = (size_t)A.blk_cap * NB * NB + 4;
     const size_t stage = (vald * 8 + (size_t)(A.blk_cap + 8) * 4 + (size_t)(B_RB + 8) * 4 + 127) & ~(size_t)127;
-    const int    nst   = 2;
+    int          nst   = c.opt.bsr_stages;
+    if (nst < 2) nst = 2;
+    if (nst > B_MAX_STAGES) nst = B_MAX_STAGES;
     const size_t smem  = stage * nst;
     static bool  attr_set = false;
     if (!attr_set) {
-        FC_CUDA(cudaFuncSetAttribute(bsr_pipe_kernel<MODE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        FC_CUDA(cudaFuncSetAttribute(bsr_pipe_kernel<MODE, NB, B_RB, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      200 * 1024));
         attr_set = true;
     }
+    if (smem > 200 * 1024) fail(ERROR_INPUT_PAR, "BSR stage ring of %zu bytes does not fit in shared memory", smem);
     int per_sm = (int)((size_t)(220 * 1024) / (smem + 4096));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 2048 / (B_RB * NB)) per_sm = 2048 / (B_RB * NB);
@@ -234,7 +322,24 @@ static void launch_nb(const DevBSR& A, const BsrView& v, const BsrArgs& a)
         part = red_partials((size_t)grid);
         tick = red_ticket();
     }
-    FC_LAUNCH((bsr_pipe_kernel<MODE, NB>), (int)grid, B_RB * NB, smem, v, a, A.nblk, nst, part, tick);
+    FC_LAUNCH((bsr_pipe_kernel<MODE, NB, B_RB, U>), (int)grid, B_RB * NB, smem, v, a, A.nblk, nst, part, tick);
+}
+
+template <int MODE, int NB>
+static void launch_nb(const DevBSR& A, const BsrView& v, const BsrArgs& a)
+{
+    if constexpr (NB <= 4) {   // the small blocks of black-oil / elasticity systems: tunable shape
+        const bool u8 = ctx().opt.bsr_u >= 8;
+        if (A.blk_rb == 64) {
+            if (u8) launch_var<MODE, NB, 64, 8>(A, v, a);
+            else launch_var<MODE, NB, 64, 4>(A, v, a);
+        } else {
+            if (u8) launch_var<MODE, NB, 32, 8>(A, v, a);
+            else launch_var<MODE, NB, 32, 4>(A, v, a);
+        }
+    } else {
+        launch_var<MODE, NB, 32, 2>(A, v, a);
+    }
 }
 
 template <int MODE>
@@ -258,7 +363,25 @@ void bsr_launch(const DevBSR& A, const BsrArgs& a)
     if (A.ROW == 0) return;
     double pbytes = bsr_spmv_bytes(A, a.mode != BSR_MXV);
     if (a.mode == BSR_JACOBI) pbytes += 8.0 * A.nb * A.nb * A.ROW;
+    if (a.mode == BSR_DINV) pbytes = 8.0 * A.nb * A.ROW * (2.0 + A.nb);
     ProfScope prof(200 + a.mode + (a.conditional ? 50 : 0), A.ROW, A.NNZ, pbytes);
+    if (a.mode == BSR_DINV) {
+        if (!a.diaginv) fail(ERROR_DATA_STRUCTURE, "block Jacobi sweep without diaginv");
+        const int g = flat_grid((long long)A.ROW * A.nb);
+        FC_LAUNCH(bsr_dinv_kernel, g, 256, 0, A.ROW, A.nb, a, red_partials(g), red_ticket());
+        return;
+    }
+    if (A.ident) {
+        switch (a.mode) {
+            case BSR_MXV: launch_ident<BSR_MXV>(A, a); return;
+            case BSR_AXPY:
+                if (a.alpha == 0.0) return;
+                launch_ident<BSR_AXPY>(A, a);
+                return;
+            case BSR_RESID: launch_ident<BSR_RESID>(A, a); return;
+            default: fail(ERROR_INPUT_PAR, "identity-block operator: mode %d is not supported", a.mode);
+        }
+    }
     BsrView   v{A.ia, A.ja, A.val, A.blkdesc, A.blk_cap, A.ROW};
     switch (a.mode) {
         case BSR_MXV: launch_mode<BSR_MXV>(A, v, a); break;
@@ -283,7 +406,7 @@ void bsr_launch(const DevBSR& A, const BsrArgs& a)
 
 // ------------------------------------------------------------------------------------
 void bsr_upload(DevBSR& d, int ROW, int COL, long long NNZ, int nb, const int* ia, const int* ja,
-                const double* val)
+                const double* val, bool detect_identity)
 {
     ensure_init();
     Ctx& c = ctx();
@@ -292,8 +415,28 @@ void bsr_upload(DevBSR& d, int ROW, int COL, long long NNZ, int nb, const int* i
     if (NNZ >= 2147483647LL / (nb * nb)) fail(ERROR_MAT_SIZE, "bsr_upload: matrix exceeds 32-bit offsets");
     d.ROW = ROW, d.COL = COL, d.NNZ = NNZ, d.nb = nb;
     const size_t pad = 8, nb2 = (size_t)nb * nb;
+    if (detect_identity && NNZ > 0) {
+        bool ident = true;
+        for (long long k = 0; k < NNZ && ident; ++k)
+            for (int e = 0; e < nb * nb; ++e)
+                if (val[(size_t)k * nb2 + e] != ((e / nb == e % nb) ? 1.0 : 0.0)) {
+                    ident = false;
+                    break;
+                }
+        d.ident = ident;
+    }
     d.ia  = dalloc<int>((size_t)ROW + 1 + pad);
     d.ja  = dalloc<int>((size_t)NNZ + pad);
+    if (d.ident) {
+        FC_CUDA(cudaMemcpyAsync(d.ia, ia, sizeof(int) * ((size_t)ROW + 1), cudaMemcpyHostToDevice, c.stream));
+        FC_CUDA(cudaMemsetAsync(d.ia + ROW + 1, 0, sizeof(int) * pad, c.stream));
+        FC_CUDA(cudaMemcpyAsync(d.ja, ja, sizeof(int) * (size_t)NNZ, cudaMemcpyHostToDevice, c.stream));
+        FC_CUDA(cudaMemsetAsync(d.ja + NNZ, 0, sizeof(int) * pad, c.stream));
+        d.bytes = sizeof(int) * ((size_t)ROW + 1 + NNZ + 2 * pad);
+        FC_CUDA(cudaStreamSynchronize(c.stream));
+        red_partials((size_t)c.sm_count * 16);
+        return;
+    }
     d.val = dalloc<double>((size_t)NNZ * nb2 + pad);
     FC_CUDA(cudaMemcpyAsync(d.ia, ia, sizeof(int) * ((size_t)ROW + 1), cudaMemcpyHostToDevice, c.stream));
     FC_CUDA(cudaMemsetAsync(d.ia + ROW + 1, 0, sizeof(int) * pad, c.stream));
@@ -302,10 +445,12 @@ void bsr_upload(DevBSR& d, int ROW, int COL, long long NNZ, int nb, const int* i
     FC_CUDA(cudaMemcpyAsync(d.val, val, sizeof(double) * (size_t)NNZ * nb2, cudaMemcpyHostToDevice, c.stream));
     FC_CUDA(cudaMemsetAsync(d.val + (size_t)NNZ * nb2, 0, sizeof(double) * pad, c.stream));
     d.bytes = sizeof(int) * ((size_t)ROW + 1 + NNZ + 2 * pad) + sizeof(double) * ((size_t)NNZ * nb2 + pad);
-    // row blocks: B_RB block rows, at most cap blocks (stage <= ~40 KB)
+    // row blocks: B_RB block rows, at most cap blocks (stage <= ~40 KB with 32 block rows, ~80 KB with 64)
+    const int B_RB = (nb <= 4 && c.opt.bsr_rb == 64) ? 64 : 32;
+    d.blk_rb       = B_RB;
     const double avg = ROW > 0 ? (double)NNZ / ROW : 1.0;
     long long    cap = (long long)(avg * B_RB + 31) / 32 * 32;
-    const long long cap_max = (long long)(40 * 1024) / (long long)(nb2 * 8 + 4) / 32 * 32;
+    const long long cap_max = (long long)(40 * 1024 * (B_RB / 32)) / (long long)(nb2 * 8 + 4) / 32 * 32;
     if (cap < 64) cap = 64;
     if (cap > cap_max) cap = cap_max;
     if (cap < 32) cap = 32;

@@ -169,6 +169,9 @@ static int* option_slot(const char* key)
     if (!strcmp(key, "wide_threads")) return &o.wide_threads;
     if (!strcmp(key, "vec_lpr")) return &o.vec_lpr;
     if (!strcmp(key, "gs_multicolor")) return &o.gs_multicolor;
+    if (!strcmp(key, "bsr_rb")) return &o.bsr_rb;
+    if (!strcmp(key, "bsr_u")) return &o.bsr_u;
+    if (!strcmp(key, "bsr_stages")) return &o.bsr_stages;
     return nullptr;
 }
 INT fasp_cuda_set_option(const char* key, double value)
@@ -267,6 +270,114 @@ INT fasp_cuda_blas_dcsr_aAxpy_agg(const REAL alpha, const dCSRmat* A, const REAL
 void fasp_cuda_blas_mxv_csr(const void* A, const REAL* x, REAL* y)
 {
     fasp_cuda_blas_dcsr_mxv(static_cast<const dCSRmat*>(A), x, y);
+}
+// fasp_solver_matfree_init (SolMatFree.c:201-235) for the formats on the device path
+INT fasp_cuda_solver_matfree_init(INT matrix_format, mxv_matfree* mf, void* A)
+{
+    if (!mf) return ERROR_INPUT_PAR;
+    switch (matrix_format) {
+        case 1: mf->fct = fasp_cuda_blas_mxv_csr; break;   // MAT_CSR
+        case 2: mf->fct = fasp_cuda_blas_mxv_bsr; break;   // MAT_BSR
+        default:
+            set_last_error("fasp_cuda_solver_matfree_init: only MAT_CSR (1) and MAT_BSR (2) are on the device path");
+            return ERROR_DATA_STRUCTURE;
+    }
+    mf->data = A;
+    return FASP_SUCCESS;
+}
+// Inverse of a dense n x n row-major matrix by the blocked Gauss-Jordan kernel that factors the coarsest AMG
+// level (dense.cu). ERROR_AMG_SETUP when a pivot falls below 1e-14 of the largest entry.
+INT fasp_cuda_dense_inverse(INT n, const REAL* a, REAL* ainv)
+{
+    API_TRY
+    ensure_init();
+    if (n < 0 || (n > 0 && (!a || !ainv))) fail(ERROR_INPUT_PAR, "fasp_cuda_dense_inverse: bad arguments");
+    if (n == 0) return FASP_SUCCESS;
+    std::vector<double> h(a, a + (size_t)n * n);
+    DenseInv D;
+    if (!dense_invert_host(D, n, h))
+        fail(ERROR_AMG_SETUP, "matrix is numerically singular (pivot below 1e-14 of the largest entry)");
+    cudaError_t e = cudaMemcpy(ainv, D.ainv, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost);
+    dense_free(D);
+    FC_CUDA(e);
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+
+// ---- BLAS-1 drop-ins (BlaArray.c), host pointers: same element-wise operations in the same
+// order as the CPU loops (bit-identical); reductions are tree sums (<= 1e-14 relative).
+INT fasp_cuda_blas_darray_ax(const INT n, const REAL a, REAL* x)
+{
+    API_TRY
+    ensure_init();
+    if (n <= 0 || a == 1.0) return FASP_SUCCESS;   // BlaArray.c:45
+    DVec dx(x, (size_t)n);
+    vec_ax(a, dx.p, (size_t)n);
+    dx.to_host(x);
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+INT fasp_cuda_blas_darray_axpy(const INT n, const REAL a, const REAL* x, REAL* y)
+{
+    API_TRY
+    ensure_init();
+    if (n <= 0) return FASP_SUCCESS;
+    DVec dx(x, (size_t)n), dy(y, (size_t)n);
+    vec_axpy(a, dx.p, dy.p, (size_t)n);
+    dy.to_host(y);
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+INT fasp_cuda_blas_darray_axpby(const INT n, const REAL a, const REAL* x, const REAL b, REAL* y)
+{
+    API_TRY
+    ensure_init();
+    if (n <= 0) return FASP_SUCCESS;
+    DVec dx(x, (size_t)n), dy(y, (size_t)n);
+    vec_axpby(a, dx.p, b, dy.p, (size_t)n);
+    dy.to_host(y);
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+REAL fasp_cuda_blas_darray_dotprod(const INT n, const REAL* x, const REAL* y)
+{
+    API_TRY
+    ensure_init();
+    if (n <= 0) return 0.0;
+    DVec dx(x, (size_t)n), dy(y, (size_t)n);
+    return vec_dot_host(dx.p, dy.p, (size_t)n);
+    API_CATCH(std::numeric_limits<double>::quiet_NaN())
+}
+REAL fasp_cuda_blas_darray_norm2(const INT n, const REAL* x)
+{
+    API_TRY
+    ensure_init();
+    if (n <= 0) return 0.0;
+    DVec dx(x, (size_t)n);
+    return vec_norm2_host(dx.p, (size_t)n);
+    API_CATCH(std::numeric_limits<double>::quiet_NaN())
+}
+REAL fasp_cuda_blas_darray_norm1(const INT n, const REAL* x)
+{
+    API_TRY
+    ensure_init();
+    if (n <= 0) return 0.0;
+    DVec   dx(x, (size_t)n);
+    double v = 0.0;
+    vec_norm1_inf_host(dx.p, (size_t)n, &v, nullptr);
+    return v;
+    API_CATCH(std::numeric_limits<double>::quiet_NaN())
+}
+REAL fasp_cuda_blas_darray_norminf(const INT n, const REAL* x)
+{
+    API_TRY
+    ensure_init();
+    if (n <= 0) return 0.0;
+    DVec   dx(x, (size_t)n);
+    double v = 0.0;
+    vec_norm1_inf_host(dx.p, (size_t)n, nullptr, &v);
+    return v;
+    API_CATCH(std::numeric_limits<double>::quiet_NaN())
 }
 
 INT fasp_cuda_smoother_dcsr_jacobi(dvector* u, const INT i_1, const INT i_n, const INT s,
@@ -796,7 +907,7 @@ INT fasp_cuda_solver_dcsr_pvgmres(dCSRmat* A, dvector* b, dvector* x, precond* p
     PrecChoice   pch;
     choose_prec(pch, pc, n);
     const int ret = gmres_solve(op, db.p, dx.p, *pch.p, tol, abstol, MaxIt, restart, StopType,
-                                PrtLvl, true, nullptr);
+                                PrtLvl, GM_VARIABLE, nullptr);
     dx.to_host(x->val);
     return ret;
     API_CATCH(code__)
@@ -836,7 +947,7 @@ INT fasp_cuda_solver_dcsr_pgmres(dCSRmat* A, dvector* b, dvector* x, precond* pc
     PrecChoice   pch;
     choose_prec(pch, pc, n);
     const int ret = gmres_solve(op, db.p, dx.p, *pch.p, tol, abstol, MaxIt, restart, StopType,
-                                PrtLvl, false, nullptr);
+                                PrtLvl, GM_FIXED, nullptr);
     dx.to_host(x->val);
     return ret;
     API_CATCH(code__)
@@ -1038,7 +1149,7 @@ struct TmpBSR {
     explicit TmpBSR(const dBSRmat* A)
     {
         check_bsr(A);
-        bsr_upload(m, A->ROW, A->COL, A->NNZ, A->nb, A->IA, A->JA, A->val);
+        bsr_upload(m, A->ROW, A->COL, A->NNZ, A->nb, A->IA, A->JA, A->val, true);
     }
     ~TmpBSR() { bsr_free(m); }
 };

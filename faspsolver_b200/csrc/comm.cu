@@ -103,11 +103,29 @@ void comm_finalize()
     n.size = 1;
 }
 
-void comm_allreduce(double* buf, size_t count, int op)
+void comm_allreduce_mixed(double* buf, int count, int maxmask, const int* gate)
 {
     if (!comm_active()) return;
     if (p2p_active() && count <= 4) {
-        p2p_allreduce(buf, (int)count, op);
+        p2p_allreduce(buf, count, maxmask, gate);
+        return;
+    }
+    // NCCL: one call per run of equal operations
+    int s = 0;
+    while (s < count) {
+        int       e  = s + 1;
+        const int mx = (maxmask >> s) & 1;
+        while (e < count && ((maxmask >> e) & 1) == mx) ++e;
+        comm_allreduce(buf + s, (size_t)(e - s), mx ? 2 : 0, gate);
+        s = e;
+    }
+}
+
+void comm_allreduce(double* buf, size_t count, int op, const int* gate)
+{
+    if (!comm_active()) return;
+    if (p2p_active() && count <= 4) {
+        p2p_allreduce(buf, (int)count, op == 2 ? 0xF : 0, gate);
         return;
     }
     Ctx& c = ctx();
@@ -117,7 +135,7 @@ void comm_allreduce(double* buf, size_t count, int op)
 }
 
 void comm_allgatherv(const double* send, size_t sendcount, double* recv, const std::vector<size_t>& counts,
-                     const std::vector<size_t>& displs)
+                     const std::vector<size_t>& displs, const int* gate)
 {
     Ctx&  c = ctx();
     Nccl& n = N();
@@ -127,7 +145,7 @@ void comm_allgatherv(const double* send, size_t sendcount, double* recv, const s
                                     c.stream));
         return;
     }
-    if (send == recv + displs[n.rank] && p2p_allgatherv(recv, counts, displs)) return;
+    if (send == recv + displs[n.rank] && p2p_allgatherv(recv, counts, displs, gate)) return;
     // variable counts: one broadcast per root inside a group (fused by NCCL into one launch)
     ProfScope prof(402, (int)sendcount, 0, 8.0 * sendcount);
     nccl_check(n.GroupStart(), "ncclGroupStart");

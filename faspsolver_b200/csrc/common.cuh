@@ -69,6 +69,9 @@ struct Options {
     int    vec_lpr          = 0;   // > 0: force this many lanes per row in the vector kernel
     int    gs_multicolor    = 0;   // accept SMOOTHER_GS in the cycle as multicolour GS (OpenMP-FASP semantics)
     int    profile          = 0;   // record CUDA events around every matrix kernel (no graphs)
+    int    bsr_rb           = 32;  // BSR pipelined kernel: block rows per CTA (32 / 64), nb <= 4
+    int    bsr_u            = 4;   // its blocks in flight per thread (4 / 8), nb <= 4
+    int    bsr_stages       = 2;   // its shared-memory stages per CTA (2..4)
 };
 
 struct Ctx {
@@ -188,9 +191,10 @@ struct Reduce {
     bool          global   = false;    // multi-GPU: the sums are all-reduced over the ranks
 };
 // all-reduce the outputs of a fused reduction when it is global and a communicator is active
-void reduce_finish(const Reduce& red);
+// (`gate`: the device flag that gated the producing kernel; the peer-memory collectives are skipped with it)
+void reduce_finish(const Reduce& red, const int* gate = nullptr);
 // ghost exchange (dist.cu); x must have room for the plan's ghosts behind its owned entries
-void halo_exchange(const HaloPlan& h, double* x);
+void halo_exchange(const HaloPlan& h, double* x, const int* gate = nullptr, bool branch = false);
 
 // ------------------------------------------------------------------------------------
 // CSR row kernels (spmv.cu)
@@ -232,6 +236,11 @@ void vec_copy(double* y, const double* x, size_t n, const int* done = nullptr);
 // y = a*x + b*y with host scalars (FASP fasp_blas_darray_axpby, BlaArray.c:620)
 void vec_axpby(double a, const double* x, double b, double* y, size_t n,
                const int* done = nullptr);
+// y += a*x (fasp_blas_darray_axpy, BlaArray.c:90) ; x *= a (fasp_blas_darray_ax, BlaArray.c:43)
+void vec_axpy(double a, const double* x, double* y, size_t n, const int* done = nullptr);
+void vec_ax(double a, double* x, size_t n, const int* done = nullptr);
+void vec_axpy_dev(const double* a_dev, const double* x, double* y, size_t n, const int* done = nullptr);
+void vec_norm1_inf_host(const double* x, size_t n, double* norm1, double* norminf);
 // y = s .* x / d  (zero-guess first sweep: L1: s=1, d=l1 ; Jacobi: s=w, d=diag)
 void vec_scale_div(double* y, double s, const double* x, const double* d, size_t n,
                    const Reduce& red = Reduce(), const int* done = nullptr);
@@ -272,8 +281,15 @@ struct CapturedGraph {
         exec  = nullptr;
         graph = nullptr;
     }
-    // First call captures `f` (stream capture, nothing executes) and instantiates it; every
-    // call then launches the instantiated graph. With enable == false, f runs directly.
+    // Capture `f` (stream capture, nothing executes) and instantiate it, without launching: lets a
+    // solver build its graphs before the timed region starts.
+    template <class F> void prepare(bool enable, F&& f)
+    {
+        if (!enable || exec) return;
+        capture(f);
+    }
+    // First call captures `f` and instantiates it (unless prepare() did); every call then launches the
+    // instantiated graph. With enable == false, f runs directly.
     template <class F> void run(bool enable, F&& f)
     {
         Ctx& c = ctx();
@@ -281,7 +297,14 @@ struct CapturedGraph {
             f();
             return;
         }
-        if (!exec) {
+        if (!exec) capture(f);
+        FC_CUDA(cudaGraphLaunch(exec, c.stream));
+        c.launches += kernels;
+    }
+    template <class F> void capture(F&& f)
+    {
+        Ctx& c = ctx();
+        {
             p2p_reset_order_hook();
             c.capturing = true;
             c.captured  = 0;
@@ -303,9 +326,8 @@ struct CapturedGraph {
             FC_CUDA(cudaStreamEndCapture(c.stream, &graph));
             kernels = c.captured;
             FC_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+            p2p_reset_order_hook();   // what the capture "exchanged last" never ran
         }
-        FC_CUDA(cudaGraphLaunch(exec, c.stream));
-        c.launches += kernels;
     }
 };
 } // namespace fc

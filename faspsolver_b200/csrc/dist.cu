@@ -21,11 +21,11 @@
 
 namespace fc {
 
-void reduce_finish(const Reduce& red)
+void reduce_finish(const Reduce& red, const int* gate)
 {
     if (!red.global || !comm_active()) return;
-    if (red.dot_out) comm_allreduce(red.dot_out, 1);
-    if (red.nrm2_out) comm_allreduce(red.nrm2_out, 1);
+    if (red.dot_out) comm_allreduce(red.dot_out, 1, 0, gate);
+    if (red.nrm2_out) comm_allreduce(red.nrm2_out, 1, 0, gate);
 }
 
 __global__ void k_halo_pack(int n, const int* __restrict__ idx, const double* __restrict__ x,
@@ -34,10 +34,10 @@ __global__ void k_halo_pack(int n, const int* __restrict__ idx, const double* __
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) buf[i] = x[idx[i]];
 }
 
-void halo_exchange(const HaloPlan& h, double* x)
+void halo_exchange(const HaloPlan& h, double* x, const int* gate, bool branch)
 {
     if (!comm_active()) return;
-    if (p2p_halo_exchange(h, x)) return;   // peer-memory push + device barrier
+    if (p2p_halo_exchange(h, x, gate, branch)) return;   // peer-memory push + device barrier
     if (h.nsend == 0 && h.nghost == 0) return;
     ProfScope prof(400, h.nloc, h.nsend + h.nghost, 8.0 * (h.nsend + h.nghost));
     if (h.nsend > 0) {
@@ -301,11 +301,7 @@ Amg* dist_amg_upload(AMG_data* mgl, AMG_param* param, int agg_rows)
         }
         h->scal = dalloc<double>(4);
         FC_CUDA(cudaMemsetAsync(h->scal, 0, 4 * sizeof(double), ctx().stream));
-        Level& C = h->lv[nl - 1];
-        if (C.n > ctx().opt.coarse_dense_max)
-            fail(ERROR_AMG_SETUP, "coarsest level has %d rows > coarse_dense_max = %d", C.n, ctx().opt.coarse_dense_max);
-        dense_invert_csr(h->coarse, C.A);
-        h->bytes += sizeof(double) * (size_t)C.n * C.n;
+        amg_setup_coarse(*h);   // replicated coarsest level: every rank factors / iterates redundantly
         FC_CUDA(cudaStreamSynchronize(ctx().stream));
     } catch (...) {
         amg_free(h);

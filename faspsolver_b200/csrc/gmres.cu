@@ -28,6 +28,7 @@ struct GmState {
     double b_norm;              // flexible variant: ||b|| as printed by ITS_PUTNORM
     int    iter, maxit, i, stop_type, variable, flexible;
     int    done, converged, silent;
+    int    notable;   // converged before the loop: the reference jumps to FINISHED without printing the table
     int    skip_inner, skip_scale, skip_true, skip_copy;
     int    R;   // leading dimension of hh: hh[j][k] = H[j * R + k]
 };
@@ -61,6 +62,10 @@ __global__ void k_gm_init(GmState* st, double* norms, double* habs)
         st->normu   = fmax(SMALLREAL, sqrt(st->xx));
         st->absres0 = st->r_norm;
         st->relres  = st->absres0 / st->normu;
+    } else if (st->stop_type == STOP_REL_PRECRES) {   // xx = (p0, B p0), KryPvgmres.c:160-167
+        const double r_normb = sqrt(st->xx);
+        st->absres0 = fmax(SMALLREAL, r_normb);
+        st->relres  = r_normb / st->absres0;
     } else {
         st->absres0 = fmax(SMALLREAL, st->r_norm);
         st->relres  = st->r_norm / st->absres0;
@@ -70,6 +75,7 @@ __global__ void k_gm_init(GmState* st, double* norms, double* habs)
     if (st->relres < st->tol || st->absres0 < st->abstol) {
         st->converged = 1;
         st->done      = 1;
+        st->notable   = 1;
     }
 }
 
@@ -239,6 +245,8 @@ __global__ void k_gm_truecheck(GmState* st, double* norms)
         if (st->stop_type == STOP_MOD_REL_RES) {
             st->normu = fmax(SMALLREAL, sqrt(st->xx));
             relres    = st->r_norm / st->normu;
+        } else if (st->stop_type == STOP_REL_PRECRES) {   // xx = (B r, r), KryPvfgmres.c:288-293
+            relres = sqrt(st->xx) / st->den_norm;
         } else {
             relres = st->r_norm / st->den_norm;
         }
@@ -255,6 +263,9 @@ __global__ void k_gm_truecheck(GmState* st, double* norms)
     if (st->stop_type == STOP_MOD_REL_RES) {
         st->normu  = fmax(SMALLREAL, sqrt(st->xx));
         st->relres = st->absres / st->normu;
+    } else if (st->stop_type == STOP_REL_PRECRES) {   // xx = (B r, r), KryPvgmres.c:312-319
+        st->absres = sqrt(st->xx);
+        st->relres = st->absres / st->absres0;
     } else {
         st->relres = st->absres / st->absres0;
     }
@@ -320,19 +331,41 @@ static int ggrid(size_t n)
     return (int)g;
 }
 
+GmresCache::~GmresCache() { release(); }
+void GmresCache::release()
+{
+    for (auto& g : step_graph) g.reset();
+    step_graph.clear();
+    start_graph.reset();
+    end_graph.reset();
+    init_graph.reset();
+    if (t0) cudaEventDestroy(t0);
+    if (t1) cudaEventDestroy(t1);
+    t0 = t1 = nullptr;
+    if (pin_h) cudaFreeHost(pin_h);
+    pin_h = nullptr;
+    dfree(pin_d);
+    pin_d = nullptr;
+    if (registered && work) p2p_unregister(work);
+    registered = false;
+    dfree(work);
+    dfree(st);
+    work = nullptr, st = nullptr;
+    n = 0, ldp = 0, R = 0, hcap = 0, kind = -1;
+}
+
 int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, double abstol,
                 int MaxIt, int restart, int StopType, int PrtLvl, int kind,
-                SolveStats* stats)
+                SolveStats* stats, GmresCache* cache)
 {
     const bool flexible = (kind == GM_FLEXIBLE);
     const bool variable = (kind == GM_VARIABLE) || flexible;   // both adapt the restart length
     ensure_init();
     Ctx&         c = ctx();
     const size_t n = (size_t)A.n;
-    if (StopType != STOP_REL_RES && StopType != STOP_MOD_REL_RES)
-        fail(ERROR_INPUT_PAR,
-             "device GMRES supports stop_type STOP_REL_RES (1) and STOP_MOD_REL_RES (3), got %d",
-             StopType);
+    const bool   precres = (StopType == STOP_REL_PRECRES);
+    if (StopType != STOP_REL_RES && StopType != STOP_MOD_REL_RES && !precres)
+        fail(ERROR_INPUT_PAR, "device GMRES: unknown stop_type %d", StopType);
     if (restart < 1) fail(ERROR_INPUT_PAR, "GMRES restart must be positive");
     if (PrtLvl > PRINT_NONE)
         printf("\nCalling %s solver (%s) ...\n", flexible ? "VFGMRes" : (variable ? "VGMRes" : "GMRes"),
@@ -344,33 +377,50 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
     const size_t    ldp         = (A.vec_capacity() + 1) & ~(size_t)1;   // room for ghosts
     const int       hcap        = MaxIt + 2;
 
-    double*   work = nullptr;
-    GmState*  st   = nullptr;
-    GmPinned *pin_d = nullptr, *pin_h = nullptr;
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
-    std::vector<CapturedGraph> step_graph(R + 1);
-    CapturedGraph              start_graph, end_graph;
-    int                        ret = 0;
+    GmresCache  local;
+    GmresCache& W = cache ? *cache : local;
+    // basis p[0..R], w, r, (flexible: z[0..R-1]) ; hh (R+1) x R, c, s, rs ; norms + absres history
+    const size_t nsmall = (size_t)(R + 1) * R + 2 * (size_t)R + (R + 1) + 2 * (size_t)hcap;
+    const size_t nvec   = (size_t)(R + 3) + (flexible ? (size_t)R : 0);
+    if (W.n != n || W.ldp != ldp || W.R != R || W.hcap != hcap || W.kind != kind) {
+        W.release();
+        W.work = dalloc<double>(nvec * ldp + nsmall);
+        if (p2p_active() && A.distributed()) {   // basis vectors are gathered by the peers' kernels
+            p2p_register(W.work, sizeof(double) * (nvec * ldp + nsmall));
+            W.registered = true;
+        }
+        W.st    = static_cast<void*>(dalloc<GmState>(1));
+        W.pin_d = static_cast<void*>(dalloc<GmPinned>(1));
+        FC_CUDA(cudaMallocHost(&W.pin_h, sizeof(GmPinned)));
+        FC_CUDA(cudaEventCreate(&W.t0));
+        FC_CUDA(cudaEventCreate(&W.t1));
+        W.step_graph.clear();
+        W.step_graph.resize(R + 1);
+        W.n = n, W.ldp = ldp, W.R = R, W.hcap = hcap, W.kind = kind;
+    }
+    // graphs bake in pointers and kernel choices: re-capture when any of them changed
+    if (W.kA != A.key() || W.kb != b || W.kx != x || W.kpc != pc.key() || W.kstop != StopType ||
+        W.kepoch != c.opt_epoch) {
+        for (auto& g : W.step_graph) g.reset();
+        W.start_graph.reset();
+        W.end_graph.reset();
+        W.init_graph.reset();
+        W.kA = A.key(), W.kb = b, W.kx = x, W.kpc = pc.key(), W.kstop = StopType;
+        W.kepoch = c.opt_epoch;
+    }
+    double*   work  = W.work;
+    GmState*  st    = static_cast<GmState*>(W.st);
+    GmPinned* pin_d = static_cast<GmPinned*>(W.pin_d);
+    GmPinned* pin_h = static_cast<GmPinned*>(W.pin_h);
+    cudaEvent_t t0 = W.t0, t1 = W.t1;
+    std::vector<CapturedGraph>& step_graph = W.step_graph;
+    CapturedGraph&              start_graph = W.start_graph;
+    CapturedGraph&              end_graph   = W.end_graph;
+    int                         ret = 0;
 
-    auto cleanup = [&]() {
-        for (auto& g : step_graph) g.reset();
-        start_graph.reset();
-        end_graph.reset();
-        if (t0) cudaEventDestroy(t0);
-        if (t1) cudaEventDestroy(t1);
-        if (pin_h) cudaFreeHost(pin_h);
-        dfree(pin_d);
-        if (work && p2p_active()) p2p_unregister(work);
-        dfree(work);
-        dfree(st);
-    };
+    auto cleanup = [&]() {};
 
     try {
-        // basis p[0..R], w, r, (flexible: z[0..R-1]) ; hh (R+1) x R, c, s, rs ; norms + absres history
-        const size_t nsmall = (size_t)(R + 1) * R + 2 * (size_t)R + (R + 1) + 2 * (size_t)hcap;
-        const size_t nvec   = (size_t)(R + 3) + (flexible ? (size_t)R : 0);
-        work       = dalloc<double>(nvec * ldp + nsmall);
-        if (p2p_active()) p2p_register(work, sizeof(double) * (nvec * ldp + nsmall));
         double* P  = work;
         double* w  = P + (size_t)(R + 1) * ldp;
         double* r  = w + ldp;
@@ -382,11 +432,6 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
         double* norms = rs + (R + 1);
         double* habs  = norms + hcap;
         FC_CUDA(cudaMemsetAsync(hh, 0, sizeof(double) * nsmall, c.stream));
-        st    = dalloc<GmState>(1);
-        pin_d = dalloc<GmPinned>(1);
-        FC_CUDA(cudaMallocHost(&pin_h, sizeof(GmPinned)));
-        FC_CUDA(cudaEventCreate(&t0));
-        FC_CUDA(cudaEventCreate(&t1));
         GmState h0;
         memset(&h0, 0, sizeof(h0));
         h0.tol = tol, h0.abstol = abstol, h0.maxit = MaxIt, h0.stop_type = StopType;
@@ -397,26 +442,30 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
         red_partials((size_t)c.sm_count * 8);
         const int  g         = ggrid(n);
         const bool use_graph = c.opt.graph && !c.opt.profile && pc.capturable();
+        const bool glob      = A.distributed();   // sums over all ranks' rows
         auto       pvec      = [&](int k) { return P + (size_t)k * ldp; };
 
-        FC_CUDA(cudaEventRecord(t0, c.stream));
-        {
+        auto initial = [&]() {
             Reduce red;
-            red.global = true;
+            red.global = glob;
             red.nrm2_out = &st->rr;
             A.apply(CSR_RESID, 1.0, x, b, pvec(0), red, nullptr);
             if (flexible || StopType == STOP_MOD_REL_RES) {
                 Reduce rx;
-                rx.global   = true;
+                rx.global   = glob;
                 rx.nrm2_out = &st->xx;
                 vec_reduce(flexible ? b : x, n, rx, nullptr);   // flexible: ||b|| (KryPvfgmres.c:150)
             }
+            if (precres && !flexible) {   // r_normb = sqrt((p0, B p0)), KryPvgmres.c:160-167
+                Reduce rz;
+                rz.global   = glob;
+                rz.dot_with = pvec(0);
+                rz.dot_out  = &st->xx;
+                pc.apply(pvec(0), r, rz, nullptr);
+            }
             FC_LAUNCH(k_gm_init, 1, 1, 0, st, norms, habs);
             FC_LAUNCH(k_gm_cycle_end, 1, 1, 0, st, pin_d);
-            FC_CUDA(cudaMemcpyAsync(pin_h, pin_d, sizeof(GmPinned), cudaMemcpyDeviceToHost, c.stream));
-            FC_CUDA(cudaStreamSynchronize(c.stream));
-        }
-
+        };
         auto inner_step = [&](int i) {
             const int* gate = &st->skip_inner;
             double* zi = flexible ? Z + (size_t)(i - 1) * ldp : r;   // flexible keeps z_{i-1} (:226-231)
@@ -426,7 +475,7 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
             {
                 FC_LAUNCH(k_gm_mgs, g, 256, 0, st, hh, j, i, j > 0 ? pvec(j - 1) : nullptr,
                           j < i ? pvec(j) : nullptr, pvec(i), n, red_partials(g), red_ticket());
-                comm_allreduce(j < i ? hh + (size_t)j * R + (i - 1) : &st->t2, 1);
+                if (glob) comm_allreduce(j < i ? hh + (size_t)j * R + (i - 1) : &st->t2, 1, 0, gate);
             }
             FC_LAUNCH(k_gm_givens, 1, 1, 0, st, hh, cc, ss, rs, norms, habs, i);
             FC_LAUNCH(k_gm_scale, g, 256, 0, st, &st->skip_scale, pvec(i), n);
@@ -447,14 +496,21 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
             FC_LAUNCH(k_gm_add, g, 256, 0, st, r, x, n);
             FC_LAUNCH(k_gm_after_update, 1, 1, 0, st);
             Reduce red;
-            red.global = true;
+            red.global = glob;
             red.nrm2_out = &st->rr;
             A.apply(CSR_RESID, 1.0, x, b, r, red, &st->skip_true, true);
             if (StopType == STOP_MOD_REL_RES) {
                 Reduce rx;
-            rx.global = true;
+            rx.global = glob;
                 rx.nrm2_out = &st->xx;
                 vec_reduce(x, n, rx, &st->skip_true);
+            }
+            if (precres) {   // (B r, r) of the true residual; the preconditioner call is gated like the residual
+                Reduce rz;
+                rz.global   = glob;
+                rz.dot_with = r;
+                rz.dot_out  = &st->xx;
+                pc.apply(r, w, rz, &st->skip_true);
             }
             FC_LAUNCH(k_gm_truecheck, 1, 1, 0, st, norms);
             vec_copy(pvec(0), r, n, &st->skip_copy);
@@ -462,6 +518,15 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
             FC_LAUNCH(k_gm_resvec, g, 256, 0, st, rs, P, ldp, n);
             FC_LAUNCH(k_gm_cycle_end, 1, 1, 0, st, pin_d);
         };
+
+        // graphs are built before the timed region (nothing executes during a capture)
+        W.init_graph.prepare(use_graph, initial);
+        start_graph.prepare(use_graph, cycle_start);
+        end_graph.prepare(use_graph, cycle_end);
+        FC_CUDA(cudaEventRecord(t0, c.stream));
+        W.init_graph.run(use_graph, initial);
+        FC_CUDA(cudaMemcpyAsync(pin_h, pin_d, sizeof(GmPinned), cudaMemcpyDeviceToHost, c.stream));
+        FC_CUDA(cudaStreamSynchronize(c.stream));
 
         int    Restart = restart_max;
         int    iter    = 0;
@@ -500,7 +565,7 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
                 printf("L2 norm of right-hand side = %.10e.\n", hs.b_norm);
                 printf("L2 norm of residual = %.10e.\n", hs.absres0);
             }
-            if (PrtLvl >= PRINT_SOME && !hs.silent) {   // a solve that stops before the loop prints no table
+            if (PrtLvl >= PRINT_SOME && !hs.silent && !hs.notable) {   // a solve that stops before the loop prints no table
                 print_itinfo(PrtLvl, StopType, 0, h2[0], hs.absres0, 0.0);
                 for (int i = 1; i < nh; ++i)
                     print_itinfo(PrtLvl, StopType, i, h2[i], h2[hcap + i], h2[i] / h2[i - 1]);

@@ -81,23 +81,35 @@ void print_final(int iter, int maxit, double relres)
 struct PcgState {
     double temp1, tp, zr, rr, alpha, beta;
     double absres0, absres, relres, normr0, normu, factor, reldiff;
-    double uinf, uu, pp;
+    double uinf, uu, pp;      // consecutive: one mixed (max, sum, sum) all-reduce
     double tol, abstol, maxdiff;
     int    iter, maxit, stop_type;
     int    done, status, converged;
-    int    skip_stag, skip_stag2, skip_cand;
+    int    skip_stag;         // != 0: the slow-convergence norms are not needed this iteration
+    int    skip_true;         // != 0: the true residual r = b - A u is not recomputed this iteration
+    int    true_kind;         // why it is: 1 stagnation restart (:229-270), 2 false-convergence guard (:277-324)
     int    zero_p, stag, more_step;
     int    divzero, n_stag_restart, n_false_conv;
+    int    init_conv;         // converged before the loop: no iteration table (KryPcg.c:156)
     int    hist_cap;
 };
 
 __device__ __forceinline__ void pcg_finish(PcgState* st, int status)
 {
-    st->status     = status;
-    st->done       = 1;
-    st->skip_stag  = 1;
-    st->skip_stag2 = 1;
-    st->skip_cand  = 1;
+    st->status    = status;
+    st->done      = 1;
+    st->skip_stag = 1;
+    st->skip_true = 1;
+}
+
+__device__ __forceinline__ double pcg_relres(const PcgState* st, double absres)
+{
+    return absres / (st->stop_type == STOP_MOD_REL_RES ? st->normu : st->normr0);
+}
+// ||r|| (or sqrt|(z,r)| for STOP_REL_PRECRES, KryPcg.c:195-203) from the device scalars
+__device__ __forceinline__ double pcg_absres(const PcgState* st)
+{
+    return st->stop_type == STOP_REL_PRECRES ? sqrt(fabs(st->zr)) : sqrt(st->rr);
 }
 
 // after r0 = b - A u0, z0 = B r0 (KryPcg.c:125-162)
@@ -110,7 +122,7 @@ __global__ void k_pcg_init(PcgState* st, double* hr, double* ha, double* hf)
         relres     = absres0 / st->normu;
         st->normr0 = absres0;
     } else {
-        absres0    = sqrt(st->rr);
+        absres0    = (st->stop_type == STOP_REL_PRECRES) ? sqrt(st->zr) : sqrt(st->rr);
         st->normr0 = fmax(SMALLREAL, absres0);
         relres     = absres0 / st->normr0;
     }
@@ -123,11 +135,12 @@ __global__ void k_pcg_init(PcgState* st, double* hr, double* ha, double* hf)
     hf[0]       = 0.0;
     if (relres < st->tol || absres0 < st->abstol) {
         st->converged = 1;
+        st->init_conv = 1;
         pcg_finish(st, 0);
     }
 }
 
-// u += alpha p ; r -= alpha t ; rr = ||r||^2          (KryPcg.c:171-188)
+// u += alpha p ; r -= alpha t ; rr = ||r||^2 with alpha = (z,r)/(t,p)          (KryPcg.c:171-188)
 __global__ void __launch_bounds__(256)
 k_pcg_update(PcgState* st, const double* __restrict__ p, const double* __restrict__ t,
              double* __restrict__ u, double* __restrict__ r, size_t n, double* partials,
@@ -137,7 +150,7 @@ k_pcg_update(PcgState* st, const double* __restrict__ p, const double* __restric
     const double tp = st->tp;
     double       v[1] = {0.0};
     if (fabs(tp) > SMALLREAL2) {
-        const double alpha = st->temp1 / tp;
+        const double alpha = st->zr / tp;   // zr still holds (z_{k-1}, r_{k-1}): the preconditioner runs later
         const double nalpha = -alpha;
         for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n;
              i += (size_t)gridDim.x * 256) {
@@ -150,32 +163,41 @@ k_pcg_update(PcgState* st, const double* __restrict__ p, const double* __restric
     grid_reduce<1, 0>(v, partials, ticket, [&](const double* s) { st->rr = s[0]; });
 }
 
+// STOP_REL_PRECRES only: the preconditioner runs before the convergence test and overwrites (z,r)
+__global__ void k_pcg_save_zr(PcgState* st)
+{
+    if (st->done) return;
+    st->temp1 = st->zr;
+}
+
 // scalar part of one iteration up to the slow-convergence test (KryPcg.c:165-212)
 __global__ void k_pcg_check(PcgState* st, double* hr, double* ha, double* hf)
 {
     if (st->done) return;
+    st->zero_p = 0;   // consumed by the previous iteration's direction update
     st->iter += 1;
     if (!(fabs(st->tp) > SMALLREAL2)) {   // possible breakdown
         st->divzero = 1;
         pcg_finish(st, 0);
         return;
     }
-    st->alpha  = st->temp1 / st->tp;
-    st->absres = sqrt(st->rr);
-    st->relres = st->absres / (st->stop_type == STOP_MOD_REL_RES ? st->normu : st->normr0);
+    const bool precres = st->stop_type == STOP_REL_PRECRES;
+    st->alpha  = (precres ? st->temp1 : st->zr) / st->tp;
+    st->absres = pcg_absres(st);
+    st->relres = pcg_relres(st, st->absres);
     st->factor = st->absres / st->absres0;
     if (st->iter < st->hist_cap) {
         hr[st->iter] = st->relres;
         ha[st->iter] = st->absres;
         hf[st->iter] = st->factor;
     }
-    st->skip_stag2 = 1;
+    st->true_kind = 0;
+    st->skip_true = 1;
     if (st->factor > 0.9) {
-        st->skip_stag = 0;
-        st->skip_cand = 1;
+        st->skip_stag = 0;   // Check I / II decide after the norms
     } else {
         st->skip_stag = 1;
-        st->skip_cand = !(st->relres < st->tol);
+        if (st->relres < st->tol) st->true_kind = 2, st->skip_true = 0;
     }
 }
 
@@ -199,7 +221,7 @@ k_pcg_stag_norms(PcgState* st, const double* __restrict__ u, const double* __res
     });
 }
 
-// Check I and the decision of Check II (KryPcg.c:215-227)
+// Check I and the decision of Check II (KryPcg.c:215-227); decides whether the true residual is needed
 __global__ void k_pcg_stag_check(PcgState* st)
 {
     if (st->done || st->skip_stag) return;
@@ -211,53 +233,51 @@ __global__ void k_pcg_stag_check(PcgState* st)
     st->normu   = sqrt(st->uu);
     st->reldiff = fabs(st->alpha) * sqrt(st->pp) / st->normu;
     if ((st->stag <= MAX_STAG) & (st->reldiff < st->maxdiff)) {
-        st->skip_stag2 = 0;   // restart: recompute r = b - A u
-    } else {
-        st->skip_cand = !(st->relres < st->tol);
+        st->true_kind = 1, st->skip_true = 0;   // restart: recompute r = b - A u
+    } else if (st->relres < st->tol) {
+        st->true_kind = 2, st->skip_true = 0;
     }
 }
 
-// after the stagnation restart's true residual (KryPcg.c:236-270)
-__global__ void k_pcg_stag_check2(PcgState* st)
-{
-    if (st->done || st->skip_stag2) return;
-    st->skip_stag2 = 1;
-    st->n_stag_restart += 1;
-    st->absres = sqrt(st->rr);
-    st->relres = st->absres / (st->stop_type == STOP_MOD_REL_RES ? st->normu : st->normr0);
-    if (st->relres < st->tol) {
-        st->converged = 1;
-        pcg_finish(st, 0);
-    } else if (st->stag >= MAX_STAG) {
-        pcg_finish(st, ERROR_SOLVER_STAG);
-    } else {
-        st->zero_p = 1;
-        st->stag += 1;
-    }
-}
-
-// Check III after the true residual has been recomputed (KryPcg.c:277-327)
-__global__ void k_pcg_cand_check(PcgState* st)
+// After the (gated) true residual: the stagnation restart (KryPcg.c:236-270) or Check III (:277-327). At most
+// one of the two recomputes r in an iteration: a restart that goes on leaves relres >= tol, which rules out Check III.
+__global__ void k_pcg_post_check(PcgState* st)
 {
     if (st->done) return;
-    if (!st->skip_cand) {
-        st->skip_cand = 1;
-        st->absres    = sqrt(st->rr);
-        st->relres = st->absres / (st->stop_type == STOP_MOD_REL_RES ? st->normu : st->normr0);
-        if (st->relres < st->tol) {
-            st->converged = 1;
-            pcg_finish(st, 0);
-            return;
+    if (!st->skip_true) {
+        st->skip_true = 1;
+        st->absres    = pcg_absres(st);
+        st->relres    = pcg_relres(st, st->absres);
+        if (st->true_kind == 1) {
+            st->n_stag_restart += 1;
+            if (st->relres < st->tol) {
+                st->converged = 1;
+                pcg_finish(st, 0);
+                return;
+            }
+            if (st->stag >= MAX_STAG) {
+                pcg_finish(st, ERROR_SOLVER_STAG);
+                return;
+            }
+            st->zero_p = 1;
+            st->stag += 1;
+        } else {
+            if (st->relres < st->tol) {
+                st->converged = 1;
+                pcg_finish(st, 0);
+                return;
+            }
+            st->n_false_conv += 1;
+            if (st->more_step >= MAX_RESTART) {
+                pcg_finish(st, ERROR_SOLVER_TOLSMALL);
+                return;
+            }
+            st->zero_p = 1;
+            st->more_step += 1;
         }
-        st->n_false_conv += 1;
-        if (st->more_step >= MAX_RESTART) {
-            pcg_finish(st, ERROR_SOLVER_TOLSMALL);
-            return;
-        }
-        st->zero_p = 1;
-        st->more_step += 1;
     }
     st->absres0 = st->absres;   // save residual for next iteration (:327)
+    if (st->stop_type != STOP_REL_PRECRES) st->temp1 = st->zr;   // the preconditioner overwrites (z,r) next
 }
 
 // p = z + beta p with beta = (z,r)/(z_old,r_old)            (KryPcg.c:337-343)
@@ -272,14 +292,6 @@ k_pcg_direction(const PcgState* st, const double* __restrict__ z, double* __rest
         const double pi = zp ? 0.0 : p[i];
         p[i]            = __dadd_rn(z[i], __dmul_rn(beta, pi));
     }
-}
-__global__ void k_pcg_end(PcgState* st)
-{
-    if (st->done) return;
-    st->beta   = st->zr / st->temp1;
-    st->temp1  = st->zr;
-    st->zero_p = 0;
-    if (st->iter >= st->maxit) st->done = 1;   // host will report ERROR_SOLVER_MAXIT
 }
 
 static int vgrid(size_t n)
@@ -320,11 +332,10 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
     Ctx&         c = ctx();
     const size_t n = (size_t)A.n;
     const size_t ncap = A.vec_capacity();   // n + room for ghost entries (multi-GPU)
-    if (StopType != STOP_REL_RES && StopType != STOP_MOD_REL_RES)
-        fail(ERROR_INPUT_PAR,
-             "device PCG supports stop_type STOP_REL_RES (1) and STOP_MOD_REL_RES (3), got %d",
-             StopType);
-    if (PrtLvl > PRINT_NONE) printf("\nCalling CG solver (CSR) ...\n");
+    if (StopType != STOP_REL_RES && StopType != STOP_REL_PRECRES && StopType != STOP_MOD_REL_RES)
+        fail(ERROR_INPUT_PAR, "device PCG: unknown stop_type %d", StopType);
+    const bool precres = (StopType == STOP_REL_PRECRES);
+    if (PrtLvl > PRINT_NONE) printf("\nCalling CG solver (%s) ...\n", A.format());
 
     PcgCache  local;
     PcgCache& W = cache ? *cache : local;
@@ -336,7 +347,7 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
         W.release();
         W.work = dalloc<double>(4 * ncap + 3 * (size_t)hcap);
         W.ncap = ncap;
-        if (p2p_active()) {   // the search direction p is gathered by the peers' level-0 kernels
+        if (p2p_active() && A.distributed()) {   // the search direction p is gathered by the peers' level-0 kernels
             p2p_register(W.work, sizeof(double) * (4 * ncap + 3 * (size_t)hcap));
             W.registered = true;
         }
@@ -373,7 +384,7 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
         h0.tol = tol, h0.abstol = abstol, h0.maxdiff = tol * STAG_RATIO;
         h0.maxit = MaxIt, h0.stop_type = StopType;
         h0.stag = 1, h0.more_step = 1;
-        h0.skip_stag = h0.skip_stag2 = h0.skip_cand = 1;
+        h0.skip_stag = h0.skip_true = 1;
         h0.hist_cap = hcap;
         h0.absres0 = h0.absres = h0.relres = h0.normu = h0.normr0 = BIGREAL;
         FC_CUDA(cudaMemcpyAsync(st, &h0, sizeof(h0), cudaMemcpyHostToDevice, c.stream));
@@ -381,63 +392,69 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
         const int* done = &st->done;
         const int  g    = vgrid(n);
         const bool use_graph = c.opt.graph && !c.opt.profile && pc.capturable();
+        const bool glob      = A.distributed();   // sums over all ranks' rows
 
-        FC_CUDA(cudaEventRecord(t0, c.stream));
-        // r = b - A u ; z = B r ; p = z ; temp1 = (z,r)
+        // r = b - A u ; z = B r ; p = z ; (z,r)
         auto initial = [&]() {
             Reduce red;
-            red.global = true;
+            red.global = glob;
             red.nrm2_out = &st->rr;
             A.apply(CSR_RESID, 1.0, u, b, r, red, nullptr);
             if (StopType == STOP_MOD_REL_RES) {
                 Reduce ru;
-            ru.global = true;
+                ru.global   = glob;
                 ru.nrm2_out = &st->uu;
                 vec_reduce(u, n, ru, nullptr);
             }
             Reduce rz;
-            rz.global = true;
+            rz.global = glob;
             rz.dot_with = r;
             rz.dot_out  = &st->zr;
             pc.apply(r, z, rz, nullptr);
             FC_LAUNCH(k_pcg_init, 1, 1, 0, st, hr, ha, hf);
             vec_copy(p, z, n, done);
         };
-        W.g_init.run(use_graph, initial);
 
+        // One iteration. Branches of the CPU loop are kernels gated by device flags; in the multi-GPU solve the
+        // ghost exchanges and all-reduces that belong to a gated kernel are skipped with it (the flags are
+        // computed from all-reduced scalars in the same order on every rank, so every rank decides alike).
         auto iteration = [&]() {
             Reduce rt;   // t = A p, tp = (t,p)
-            rt.global = true;
+            rt.global = glob;
             rt.dot_with = p;
             rt.dot_out  = &st->tp;
             A.apply(CSR_MXV, 1.0, p, nullptr, t, rt, done);
             FC_LAUNCH(k_pcg_update, g, 256, 0, st, p, t, u, r, n, red_partials(g), red_ticket());
-            comm_allreduce(&st->rr, 1);
+            Reduce rz;   // z = B r, (z,r)
+            rz.global = glob;
+            rz.dot_with = r;
+            rz.dot_out  = &st->zr;
+            if (precres) {   // the stopping test needs (B r, r): precondition first (KryPcg.c:195-203)
+                FC_LAUNCH(k_pcg_save_zr, 1, 1, 0, st);
+                pc.apply(r, z, rz, done);
+            } else {
+                if (glob) comm_allreduce(&st->rr, 1, 0, done);
+            }
             FC_LAUNCH(k_pcg_check, 1, 1, 0, st, hr, ha, hf);
             // slow convergence: stagnation test and possible restart
             FC_LAUNCH(k_pcg_stag_norms, g, 256, 0, st, u, p, n, red_partials(g), red_ticket());
-            if (comm_active()) {   // branch-gated kernel: the flags are identical on every rank
-                comm_allreduce(&st->uinf, 1, 2);
-                comm_allreduce(&st->uu, 2, 0);
-            }
+            if (glob) comm_allreduce_mixed(&st->uinf, 3, 0x1, &st->skip_stag);
             FC_LAUNCH(k_pcg_stag_check, 1, 1, 0, st);
+            // true residual, for the stagnation restart or the false-convergence guard
             Reduce rr;
-            rr.global = true;
+            rr.global = glob;
             rr.nrm2_out = &st->rr;
-            A.apply(CSR_RESID, 1.0, u, b, r, rr, &st->skip_stag2, true);
-            FC_LAUNCH(k_pcg_stag_check2, 1, 1, 0, st);
-            // false-convergence guard: true residual
-            A.apply(CSR_RESID, 1.0, u, b, r, rr, &st->skip_cand, true);
-            FC_LAUNCH(k_pcg_cand_check, 1, 1, 0, st);
-            // z = B r, zr = (z,r)
-            Reduce rz;
-            rz.global = true;
-            rz.dot_with = r;
-            rz.dot_out  = &st->zr;
-            pc.apply(r, z, rz, done);
+            A.apply(CSR_RESID, 1.0, u, b, r, rr, &st->skip_true, true);
+            if (precres) pc.apply(r, z, rz, &st->skip_true);
+            FC_LAUNCH(k_pcg_post_check, 1, 1, 0, st);
+            if (!precres) pc.apply(r, z, rz, done);
             FC_LAUNCH(k_pcg_direction, g, 256, 0, st, z, p, n);
-            FC_LAUNCH(k_pcg_end, 1, 1, 0, st);
         };
+        // graphs are built before the timed region (a capture executes nothing)
+        W.g_init.prepare(use_graph, initial);
+        W.g_iter.prepare(use_graph, iteration);
+        FC_CUDA(cudaEventRecord(t0, c.stream));
+        W.g_init.run(use_graph, initial);
 
         bool finished = false;
         for (int it = 1; it <= MaxIt && !finished; ++it) {
@@ -463,7 +480,7 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
             const int           nh = (hs.iter + 1 < hcap) ? hs.iter + 1 : hcap;
             std::vector<double> h3(3 * (size_t)hcap);
             FC_CUDA(cudaMemcpy(h3.data(), hr, sizeof(double) * 3 * hcap, cudaMemcpyDeviceToHost));
-            if (PrtLvl >= PRINT_SOME)
+            if (PrtLvl >= PRINT_SOME && !hs.init_conv)
                 for (int i = 0; i < nh; ++i)
                     print_itinfo(PrtLvl, StopType, i, h3[i], h3[hcap + i], h3[2 * hcap + i]);
             if (stats) {

@@ -12,6 +12,10 @@ struct LinOp {
     virtual const void* key() const { return this; }   // identity of the resident operator
     virtual size_t      vec_capacity() const { return (size_t)n; }   // entries a gathered vector must hold
     virtual const char* format() const { return "CSR"; }             // name in the "Calling ... solver" line
+    // rows partitioned over the ranks: dot products / norms of the Krylov loop are all-reduced. A plain
+    // single-GPU operator stays local even while a communicator is active (rank 0 of a multi-GPU job can
+    // run the one-GPU solve next to the partitioned one: bench.py's parity line).
+    virtual bool        distributed() const { return false; }
     // mode: CSR_MXV / CSR_AXPY / CSR_RESID semantics
     virtual void apply(int mode, double alpha, const double* x, const double* b, double* y,
                        const Reduce& red, const int* done, bool conditional = false) = 0;
@@ -20,6 +24,7 @@ struct CsrOp : LinOp {
     const DevCSR* A;
     explicit CsrOp(const DevCSR* a) : A(a) { n = a->rows; }
     const void* key() const override { return A; }
+    bool        distributed() const override { return A->halo != nullptr; }
     size_t      vec_capacity() const override
     {
         return A->vec_cap > 0 ? (size_t)A->vec_cap : (size_t)A->rows + (size_t)A->nghost;
@@ -134,6 +139,26 @@ struct PcgCache {
     void release();
 };
 
+// The same for GMRES: basis / Hessenberg workspace, state, pinned status word and one captured graph per
+// inner-step index (the basis pointers are baked into the nodes) survive across solves, so a repeated
+// solve allocates, captures and instantiates nothing.
+struct GmresCache {
+    double* work = nullptr;
+    void*   st   = nullptr;
+    void *  pin_d = nullptr, *pin_h = nullptr;
+    size_t  n = 0, ldp = 0;
+    int     R = 0, hcap = 0, kind = -1;
+    bool    registered = false;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    std::vector<CapturedGraph> step_graph;
+    CapturedGraph start_graph, end_graph, init_graph;
+    const void *  kA = nullptr, *kb = nullptr, *kx = nullptr, *kpc = nullptr;
+    int           kstop = 0;
+    long long     kepoch = -1;
+    ~GmresCache();
+    void release();
+};
+
 // All vectors are device pointers. Returns FASP status (>=0 iterations, <0 ERROR_*).
 int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double abstol,
               int MaxIt, int StopType, int PrtLvl, SolveStats* stats, PcgCache* cache = nullptr);
@@ -142,7 +167,7 @@ int pcg_solve(LinOp& A, const double* b, double* u, Prec& pc, double tol, double
 enum { GM_FIXED = 0, GM_VARIABLE = 1, GM_FLEXIBLE = 2 };
 int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, double abstol,
                 int MaxIt, int restart, int StopType, int PrtLvl, int kind,
-                SolveStats* stats);
+                SolveStats* stats, GmresCache* cache = nullptr);
 
 // FASP's iteration table / final line (AuxMessage.c:41-76, KryUtil.inl:93-103)
 void print_itinfo(int prtlvl, int stop_type, int iter, double relres, double absres,

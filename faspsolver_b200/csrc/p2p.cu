@@ -227,7 +227,11 @@ __device__ __forceinline__ unsigned long long barrier_body(P2PCtrl* me, const Pe
     return e;
 }
 
-__global__ void k_p2p_barrier(P2PCtrl* me, PeerCtrls peers, int rank, int n) { barrier_body(me, peers, rank, n); }
+__global__ void k_p2p_barrier(P2PCtrl* me, PeerCtrls peers, int rank, int n, const int* gate)
+{
+    if (gate != nullptr && *gate != 0) return;   // the same decision on every rank
+    barrier_body(me, peers, rank, n);
+}
 
 struct PushDst {
     double* dst[P2P_MAX_RANKS];   // per send segment: where it lands in the peer's vector
@@ -235,8 +239,9 @@ struct PushDst {
     int     nseg;
 };
 __global__ void __launch_bounds__(256)
-k_halo_push(int n, const int* __restrict__ idx, const double* __restrict__ x, PushDst d)
+k_halo_push(int n, const int* __restrict__ idx, const double* __restrict__ x, PushDst d, const int* gate)
 {
+    if (gate != nullptr && *gate != 0) return;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int s = 0;
         while (s + 1 < d.nseg && i >= d.off[s + 1]) ++s;
@@ -244,8 +249,10 @@ k_halo_push(int n, const int* __restrict__ idx, const double* __restrict__ x, Pu
     }
 }
 
-__global__ void k_p2p_allreduce(P2PCtrl* me, PeerCtrls peers, int rank, int n, double* buf, int count, int op)
+__global__ void k_p2p_allreduce(P2PCtrl* me, PeerCtrls peers, int rank, int n, double* buf, int count, int maxmask,
+                                const int* gate)
 {
+    if (gate != nullptr && *gate != 0) return;
     const int                q  = threadIdx.x;
     const unsigned long long e1 = me->epoch + 1;   // parity of the epoch this barrier will reach
     const int                par = (int)(e1 & 1ULL);
@@ -256,7 +263,7 @@ __global__ void k_p2p_allreduce(P2PCtrl* me, PeerCtrls peers, int rank, int n, d
         double acc = me->slots[par][0][q];
         for (int r = 1; r < n; ++r) {
             const double v = me->slots[par][r][q];
-            acc            = (op == 2) ? (acc > v ? acc : v) : acc + v;
+            acc            = ((maxmask >> q) & 1) ? (acc > v ? acc : v) : acc + v;
         }
         buf[q] = acc;
     }
@@ -266,8 +273,10 @@ struct GatherDst {
     double* dst[P2P_MAX_RANKS];
     int     n;
 };
-__global__ void __launch_bounds__(256) k_p2p_gather_push(const double* __restrict__ src, size_t cnt, GatherDst d)
+__global__ void __launch_bounds__(256)
+k_p2p_gather_push(const double* __restrict__ src, size_t cnt, GatherDst d, const int* gate)
 {
+    if (gate != nullptr && *gate != 0) return;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (size_t)gridDim.x * blockDim.x) {
         const double v = src[i];
         for (int q = 0; q < d.n; ++q) d.dst[q][i] = v;
@@ -281,14 +290,14 @@ static PeerCtrls peer_ctrls()
     return pc;
 }
 
-void p2p_barrier()
+void p2p_barrier(const int* gate)
 {
     State& s = S();
     if (!s.on) return;
-    FC_LAUNCH(k_p2p_barrier, 1, 32, 0, s.ctrl, peer_ctrls(), s.rank, s.size);
+    FC_LAUNCH(k_p2p_barrier, 1, 32, 0, s.ctrl, peer_ctrls(), s.rank, s.size, gate);
 }
 
-bool p2p_halo_exchange(const HaloPlan& h, double* x)
+bool p2p_halo_exchange(const HaloPlan& h, double* x, const int* gate, bool branch)
 {
     State& s = S();
     if (!s.on || !h.p2p_ready) return false;
@@ -297,8 +306,9 @@ bool p2p_halo_exchange(const HaloPlan& h, double* x)
     ProfScope prof(400, h.nloc, h.nsend + h.nghost, 8.0 * (h.nsend + h.nghost));
     // the previous exchange's barrier only guarantees that every rank finished the kernel BEFORE it;
     // pushing into the vector that kernel is still reading on a slower rank needs one more barrier
-    if (s.last_exchanged == x || s.last_exchanged == nullptr) p2p_barrier();
-    s.last_exchanged = x;
+    if (s.last_exchanged == x || s.last_exchanged == nullptr) p2p_barrier(gate);
+    // an exchange behind a branch flag may not run: whatever follows must not count on it
+    s.last_exchanged = branch ? nullptr : x;
     if (h.nsend > 0) {
         PushDst d;
         d.nseg = (int)h.send_peer.size();
@@ -309,27 +319,28 @@ bool p2p_halo_exchange(const HaloPlan& h, double* x)
         d.off[d.nseg] = h.nsend;
         int g = (h.nsend + 255) / 256;
         if (g > 592) g = 592;
-        FC_LAUNCH(k_halo_push, g, 256, 0, h.nsend, h.send_idx, x, d);
+        FC_LAUNCH(k_halo_push, g, 256, 0, h.nsend, h.send_idx, x, d, gate);
     }
-    p2p_barrier();
+    p2p_barrier(gate);
     return true;
 }
 
-void p2p_allreduce(double* buf, int count, int op)
+void p2p_allreduce(double* buf, int count, int maxmask, const int* gate)
 {
     State& s = S();
     ProfScope prof(401, count, 0, 8.0 * count);
-    FC_LAUNCH(k_p2p_allreduce, 1, 32, 0, s.ctrl, peer_ctrls(), s.rank, s.size, buf, count, op);
+    FC_LAUNCH(k_p2p_allreduce, 1, 32, 0, s.ctrl, peer_ctrls(), s.rank, s.size, buf, count, maxmask, gate);
 }
 
-bool p2p_allgatherv(double* full, const std::vector<size_t>& counts, const std::vector<size_t>& displs)
+bool p2p_allgatherv(double* full, const std::vector<size_t>& counts, const std::vector<size_t>& displs,
+                    const int* gate)
 {
     State& s = S();
     if (!s.on) return false;
     double* peer[P2P_MAX_RANKS];
     if (!p2p_lookup(full, peer)) return false;
     ProfScope prof(402, (int)counts[s.rank], 0, 8.0 * counts[s.rank]);
-    if (s.last_exchanged == full || s.last_exchanged == nullptr) p2p_barrier();
+    if (s.last_exchanged == full || s.last_exchanged == nullptr) p2p_barrier(gate);
     s.last_exchanged = full;
     GatherDst d;
     d.n = 0;
@@ -339,9 +350,9 @@ bool p2p_allgatherv(double* full, const std::vector<size_t>& counts, const std::
     if (cnt > 0 && d.n > 0) {
         int g = (int)((cnt + 255) / 256);
         if (g > 592) g = 592;
-        FC_LAUNCH(k_p2p_gather_push, g, 256, 0, full + displs[s.rank], cnt, d);
+        FC_LAUNCH(k_p2p_gather_push, g, 256, 0, full + displs[s.rank], cnt, d, gate);
     }
-    p2p_barrier();
+    p2p_barrier(gate);
     return true;
 }
 

@@ -32,11 +32,16 @@ void p2p_allgather_ints(const std::vector<int>& mine, std::vector<int>& all);
 void p2p_reset_order();   // forget the last exchanged vector (start of a captured graph)
 int  p2p_error();         // nonzero if a device-side wait ran out of its spin budget
 // push-based ghost exchange + barrier; returns false if x is not peer-mapped (caller uses NCCL)
-bool p2p_halo_exchange(const HaloPlan& h, double* x);
-// in-place all-reduce of <= 4 doubles (op 0 sum, 2 max)
-void p2p_allreduce(double* buf, int count, int op);
+// `gate` (device flag, identical on every rank): the kernels of the exchange return at once when *gate != 0,
+// on all ranks alike, so a skipped exchange costs launches but no NVLink round trip and the barrier epochs stay
+// in step. `branch` marks a gate that is a rarely-taken branch flag rather than the solver's `done` flag: the
+// exchange may or may not run, so the next exchange must not rely on it having separated two pushes.
+bool p2p_halo_exchange(const HaloPlan& h, double* x, const int* gate = nullptr, bool branch = false);
+// in-place all-reduce of <= 4 doubles; bit s of maxmask makes slot s a max-reduction (others are sums)
+void p2p_allreduce(double* buf, int count, int maxmask, const int* gate = nullptr);
 // every rank's slice [displs[r], +counts[r]) of `full` is filled from its owner
-bool p2p_allgatherv(double* full, const std::vector<size_t>& counts, const std::vector<size_t>& displs);
-void p2p_barrier();
+bool p2p_allgatherv(double* full, const std::vector<size_t>& counts, const std::vector<size_t>& displs,
+                    const int* gate = nullptr);
+void p2p_barrier(const int* gate = nullptr);
 
 } // namespace fc

@@ -104,6 +104,7 @@ void solver_destroy(fasp_cuda_solver_s* s)
     }
     s->hostreg.clear();
     s->pcg_cache.release();
+    s->gmres_cache.release();
     if (s->x_registered) p2p_unregister(s->d_x);
     amg_free(s->amg);
     bamg_free(s->bamg);
@@ -122,13 +123,13 @@ static int run_krylov(fasp_cuda_solver_s* s, LinOp& op, Prec& pc, const double* 
                              it->print_level, &s->stats, &s->pcg_cache);
         case SOLVER_GMRES:
             return gmres_solve(op, b_dev, x_dev, pc, it->tol, it->abstol, it->maxit, it->restart,
-                               it->stop_type, it->print_level, GM_FIXED, &s->stats);
+                               it->stop_type, it->print_level, GM_FIXED, &s->stats, &s->gmres_cache);
         case SOLVER_VGMRES:
             return gmres_solve(op, b_dev, x_dev, pc, it->tol, it->abstol, it->maxit, it->restart,
-                               it->stop_type, it->print_level, GM_VARIABLE, &s->stats);
+                               it->stop_type, it->print_level, GM_VARIABLE, &s->stats, &s->gmres_cache);
         case SOLVER_VFGMRES:
             return gmres_solve(op, b_dev, x_dev, pc, it->tol, it->abstol, it->maxit, it->restart,
-                               it->stop_type, it->print_level, GM_FLEXIBLE, &s->stats);
+                               it->stop_type, it->print_level, GM_FLEXIBLE, &s->stats, &s->gmres_cache);
         default:
             fail(ERROR_SOLVER_TYPE,
                  "itsolver_type %d not on the device path (supported: CG 1, GMRES 4, VGMRES 5, VFGMRES 6)",
@@ -142,7 +143,16 @@ int solver_solve_dev(fasp_cuda_solver_s* s, const double* b_dev, double* x_dev, 
     if (s->amg) {
         CsrOp     op(&s->amg->lv[0].A);
         AmgPrec   pc(s->amg);
-        const int ret = run_krylov(s, op, pc, b_dev, x_dev, it);
+        // Row-partitioned hierarchy: x is gathered by the level-0 kernels (true residual), so it needs
+        // room for the ghost entries behind its owned part and must be peer-mapped. A caller vector of
+        // exactly n_local doubles has neither: stage it through the solver's own x buffer.
+        const bool stage_x = s->amg->dist && x_dev != s->d_x;
+        double*    x_run   = stage_x ? s->d_x : x_dev;
+        if (stage_x)
+            FC_CUDA(cudaMemcpyAsync(s->d_x, x_dev, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, ctx().stream));
+        const int ret = run_krylov(s, op, pc, b_dev, x_run, it);
+        if (stage_x)
+            FC_CUDA(cudaMemcpyAsync(x_dev, s->d_x, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, ctx().stream));
         if (p2p_active() && p2p_error())
             fail(ERROR_SOLVER_MISC, "multi-GPU barrier timed out (a rank fell out of step)");
         return ret;

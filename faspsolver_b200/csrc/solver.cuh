@@ -11,6 +11,7 @@ struct fasp_cuda_solver_s {
     fc::BAmg*      bamg = nullptr;     // or a BSR hierarchy
     fc::SolveStats stats;
     fc::PcgCache   pcg_cache;      // workspace + graphs reused across solves
+    fc::GmresCache gmres_cache;    // the same for GMRES / vGMRES / vFGMRES
     double         ms_total = 0.0;     // last solve incl. H2D/D2H
     double*        d_b = nullptr;      // staging vectors for host-pointer solves
     double*        d_x = nullptr;

@@ -588,13 +588,18 @@ static void launch_mode(const DevCSR& A, const CsrView& v, const CsrArgs& a)
 
 void csr_launch(const DevCSR& A, const CsrArgs& a_in)
 {
-    if (A.rows == 0) return;
+    if (A.rows == 0) {
+        // a rank that owns no row of this operator still takes part in the collectives around the kernel
+        if (A.halo) halo_exchange(*A.halo, const_cast<double*>(a_in.x), a_in.done, a_in.conditional);
+        vec_reduce(a_in.y, 0, a_in.red, a_in.done);   // zero contribution (+ the all-reduce)
+        return;
+    }
     const bool reads_y = (a_in.mode == CSR_AXPY || a_in.mode == CSR_RESID || a_in.mode >= CSR_JACOBI);
     double     pbytes  = csr_spmv_bytes(A, reads_y);
     if (a_in.mode == CSR_JACOBI || a_in.mode == CSR_L1) pbytes += 16.0 * A.rows;   // + u read, d read
     if (a_in.mode >= CSR_POLY1) pbytes += 16.0 * A.rows;
     const CsrArgs& a = a_in;
-    if (A.halo) halo_exchange(*A.halo, const_cast<double*>(a.x));
+    if (A.halo) halo_exchange(*A.halo, const_cast<double*>(a.x), a.done, a.conditional);
     ProfScope  prof(a.conditional ? a.mode + 50 : a.mode, A.rows, A.nnz, pbytes);
     CsrView v{A.ia, A.ja, A.val, A.rowblk, A.blkdesc, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap, ctx().opt.rowwise_max};
     switch (a.mode) {
@@ -616,7 +621,7 @@ void csr_launch(const DevCSR& A, const CsrArgs& a_in)
         case CSR_RESID_DINV: launch_mode<CSR_RESID_DINV>(A, v, a); break;
         default: fail(ERROR_INPUT_PAR, "csr_launch: unknown mode %d", a.mode);
     }
-    reduce_finish(a.red);
+    reduce_finish(a.red, a.done);
 }
 
 // ------------------------------------------------------------------------------------

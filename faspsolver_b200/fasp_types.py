@@ -1,8 +1,8 @@
 """ctypes mirrors of the FASP structs that cross the libfasp_cuda boundary.
 
 Same member names and order as include/fasp_cuda_types.h (which mirrors base/include/fasp.h
-and fasp_block.h of FASP 2.8.7, sequential ABI). tests/test_abi.py checks the sizes against
-the C header.
+and fasp_block.h of FASP 2.8.7, sequential ABI). tests/test_boundary.py checks the sizes against
+the C header and the reference's own headers.
 """
 from __future__ import annotations
 
@@ -141,6 +141,17 @@ PRECOND_FCT = C.CFUNCTYPE(None, PREAL, PREAL, C.c_void_p)
 
 class precond(C.Structure):
     _fields_ = [("data", C.c_void_p), ("fct", PRECOND_FCT)]
+
+
+MXV_FCT = C.CFUNCTYPE(None, C.c_void_p, PREAL, PREAL)
+
+
+class mxv_matfree(C.Structure):
+    """fasp.h:1109-1117"""
+    _fields_ = [("data", C.c_void_p), ("fct", MXV_FCT)]
+
+
+MAT_CSR, MAT_BSR = 1, 2
 
 
 # ---- numpy <-> struct helpers ------------------------------------------------------------

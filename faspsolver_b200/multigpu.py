@@ -85,6 +85,93 @@ class DistSolver(api.KrylovAmgSolver):
 
 
 # ---------------------------------------------------------------------------------------
+# one host hierarchy per node
+# ---------------------------------------------------------------------------------------
+class SharedHierarchy:
+    """FASP's host setup runs on rank 0 only; the CSR arrays of every level (A, P, R) are written once to a
+    shared-memory directory and mapped read-only by the other ranks, which wrap them in an AMG_data array
+    (fasp.h:804-888) for fasp_cuda_dist_krylov_amg_create. Falls back to one setup per rank when no shared
+    directory has room. The AMG_param mutations of the setup (PreAMGSetupRS.c:83) are broadcast with it."""
+
+    def __init__(self, hf, A, amg, rank, world, root=None):
+        import shutil
+        import tempfile
+        import torch.distributed as dist
+        self.hf, self.amg, self.rank, self.owner, self.dir = hf, amg, rank, False, None
+        self._keep = []
+        if world == 1:
+            self.mgl, self.how, self.owner = hf.amg_setup(A, amg), "FASP sequential setup", True
+            return
+        box = [None]
+        if rank == 0:
+            need = 16.0 * A.nnz * 6.0   # generous bound on the bytes of all levels
+            for cand in ([root] if root else []) + ["/dev/shm", tempfile.gettempdir()]:
+                try:
+                    if shutil.disk_usage(cand).free > 1.3 * need:
+                        box[0] = tempfile.mkdtemp(prefix="fasp_hier_", dir=cand)
+                        break
+                except OSError:
+                    continue
+        dist.broadcast_object_list(box, src=0)
+        if box[0] is None:   # no room anywhere: every rank runs the (deterministic) setup itself
+            self.mgl, self.how, self.owner = hf.amg_setup(A, amg), "FASP sequential setup on every rank", True
+            return
+        self.dir = box[0]
+        meta = [None]
+        if rank == 0:
+            self.mgl, self.owner = hf.amg_setup(A, amg), True
+            nl = self.mgl[0].num_levels
+            shapes = []
+            for l in range(nl):
+                lv = {}
+                for nm in ("A", "P", "R"):
+                    if nm != "A" and l == nl - 1:
+                        continue
+                    m = getattr(self.mgl[l], nm)
+                    lv[nm] = (int(m.row), int(m.col), int(m.nnz), bool(m.val))
+                    np.save(os.path.join(self.dir, "%d%s_ia.npy" % (l, nm)), np.ctypeslib.as_array(m.IA, shape=(m.row + 1,)))
+                    if m.nnz:
+                        np.save(os.path.join(self.dir, "%d%s_ja.npy" % (l, nm)), np.ctypeslib.as_array(m.JA, shape=(m.nnz,)))
+                        if m.val:
+                            np.save(os.path.join(self.dir, "%d%s_val.npy" % (l, nm)),
+                                    np.ctypeslib.as_array(m.val, shape=(m.nnz,)))
+                shapes.append(lv)
+            meta[0] = (nl, shapes, bytes(amg))
+        dist.broadcast_object_list(meta, src=0)
+        nl, shapes, amg_bytes = meta[0]
+        C.memmove(C.byref(amg), amg_bytes, C.sizeof(amg))
+        self.how = "FASP sequential setup on rank 0, mapped read-only by the other ranks from %s" % os.path.dirname(self.dir)
+        if rank != 0:
+            arr = (T.AMG_data * max(int(amg.max_levels), nl))()
+            for l, lv in enumerate(shapes):
+                for nm, (row, col, nnz, has_val) in lv.items():
+                    ia = np.load(os.path.join(self.dir, "%d%s_ia.npy" % (l, nm)), mmap_mode="r")
+                    ja = np.load(os.path.join(self.dir, "%d%s_ja.npy" % (l, nm)), mmap_mode="r") if nnz else None
+                    va = np.load(os.path.join(self.dir, "%d%s_val.npy" % (l, nm)), mmap_mode="r") if (nnz and has_val) else None
+                    self._keep += [ia, ja, va]
+                    m = T.dCSRmat(row, col, nnz, C.cast(ia.ctypes.data, T.PINT),
+                                  C.cast(ja.ctypes.data, T.PINT) if ja is not None else None,
+                                  C.cast(va.ctypes.data, T.PREAL) if va is not None else None)
+                    setattr(arr[l], nm, m)
+            arr[0].num_levels = nl
+            arr[0].max_levels = max(int(amg.max_levels), nl)
+            self.mgl = arr
+
+    def close(self):
+        import shutil
+        import torch.distributed as dist
+        if self.owner:
+            self.hf.amg_free(self.mgl, self.amg)
+        self.mgl = None
+        self._keep = []
+        if self.dir is not None:
+            if dist.is_initialized():
+                dist.barrier()
+            if self.rank == 0:
+                shutil.rmtree(self.dir, ignore_errors=True)
+
+
+# ---------------------------------------------------------------------------------------
 # bench.py --gpus N
 # ---------------------------------------------------------------------------------------
 def bench_main(args):
@@ -97,18 +184,24 @@ def bench_main(args):
     log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
 
     hf = B.host_fasp()
-    A, b = B.build_problem(args.n) if rank == 0 else _quiet(B.build_problem, args.n)
-    n = A.shape[0]
+    if rank == 0:
+        A, b = B.build_problem(args.n)
+        n = A.shape[0]
+    else:   # only rank 0 needs the global matrix (setup, true residual); b = 1 everywhere
+        A, n = None, args.n ** 3
+        b = np.ones(n)
     amg, it = B.amg_recipe(hf)
     t = time.time()
-    mgl = hf.amg_setup(A, amg)          # every rank builds the same hierarchy (deterministic host setup)
+    # the host hierarchy is built ONCE per node: rank 0 runs FASP's setup, the other ranks map its arrays
+    # read-only from shared memory (each rank only uploads its own row slabs of it)
+    shared = SharedHierarchy(hf, A, amg, rank, world)
+    mgl = shared.mgl
     t_setup = time.time() - t
     info = api.hierarchy_info(mgl)
-    log("[bench] host AMG setup on every rank: %.1fs, %d levels" % (t_setup, len(info)))
+    log("[bench] host AMG setup (%s): %.1fs, %d levels" % (shared.how, t_setup, len(info)))
     t = time.time()
     solver = DistSolver(mgl, amg, agg_rows=args.agg_rows)
     t_upload = time.time() - t
-    hf.amg_free(mgl, amg)
     r0, r1 = solver.row0, solver.row1
     nloc = r1 - r0
     b_loc = np.ascontiguousarray(b[r0:r1])
@@ -178,6 +271,16 @@ def bench_main(args):
         true_rel = float(np.linalg.norm(b - A.to_scipy() @ x) / np.linalg.norm(b))
         if not true_rel <= 1e-8 * 1.001:
             raise RuntimeError("assembled solution misses the tolerance: %g" % true_rel)
+        # N > 1 parity, visible to the driver: rank 0 also runs the ONE-GPU solve on the same hierarchy and
+        # compares (the other ranks wait at the barrier below); the bench fails if the solutions differ
+        s1 = api.KrylovAmgSolver(mgl, amg)
+        it1, x1 = s1.solve(b, np.zeros(n), it)
+        s1.close()
+        dx = float(np.linalg.norm(x - x1) / np.linalg.norm(x1))
+        parity = {"iters_1": int(it1), "iters_N": int(iters), "dx_rel": dx, "bar": "|iters_N - iters_1| <= 1, dx_rel <= 1e-8"}
+        log("[bench] parity vs the one-GPU solve: %s" % parity)
+        if it1 < 0 or abs(int(iters) - int(it1)) > 1 or not dx <= 1e-8:
+            raise RuntimeError("multi-GPU solve differs from the one-GPU solve: %s" % parity)
         ms = float(np.mean(dev_ms))
         out = {
             "metric": B.METRIC, "value": ms, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
@@ -187,18 +290,21 @@ def bench_main(args):
                                    "classical RS (FASP host setup), V(1,1) L1-Jacobi; rows partitioned over %d GPUs, "
                                    "levels below %d rows replicated" % (args.n, n, A.nnz, world, args.agg_rows),
                        "levels": len(info), "iterations": int(iters), "true_relres": true_rel,
-                       "l2_policy": "inputs larger than L2", "setup_s_host": t_setup, "upload_s": t_upload,
+                       "l2_policy": "inputs larger than L2", "setup_s_host": t_setup, "setup_how": shared.how,
+                       "upload_s": t_upload,
                        "parallelism": ("row slabs x%d, ghost push + flag barrier + all-reduce over peer-mapped memory (NVLink)"
                                        if L.fasp_cuda_comm_peer_memory() else
                                        "row slabs x%d, NCCL halo send/recv + allreduce") % world},
             "e2e": {"value": float(np.mean(e2e_ms)), "unit": B.UNIT, "h2d_bytes_per_step": int(16 * nloc),
                     "d2h_bytes_per_step": int(8 * nloc)},
             "gpu_launches": launches, "clocks": clocks,
-            "roofline": roofline, "cpu_baseline": None,
+            "roofline": roofline, "cpu_baseline": None, "parity": parity,
         }
+    barrier()
     api.unpin_host(b_loc)
     api.unpin_host(x_buf)
     solver.close()
+    shared.close()
     L.fasp_cuda_comm_finalize()
     return out
 

@@ -103,10 +103,33 @@ INT fasp_cuda_blas_dbsr_mxv(const dBSRmat* A, const REAL* x, REAL* y);
 /* y = y + alpha*A*x (block CSR).   replaces fasp_blas_dbsr_aAxpy    BlaSpmvBSR.c:514 */
 INT fasp_cuda_blas_dbsr_aAxpy(const REAL alpha, const dBSRmat* A, const REAL* x, REAL* y);
 
+/* BLAS-1 with host pointers (BlaArray.c). Element-wise results are bit-identical to the CPU
+ * loops; the reductions return NaN on failure and agree to <= 1e-14 relative (tree sums).
+ * x = a*x.                         replaces fasp_blas_darray_ax       BlaArray.c:43  */
+INT fasp_cuda_blas_darray_ax(const INT n, const REAL a, REAL* x);
+/* y = a*x + y.                     replaces fasp_blas_darray_axpy     BlaArray.c:90  */
+INT fasp_cuda_blas_darray_axpy(const INT n, const REAL a, const REAL* x, REAL* y);
+/* y = a*x + b*y.                   replaces fasp_blas_darray_axpby    BlaArray.c:620 */
+INT fasp_cuda_blas_darray_axpby(const INT n, const REAL a, const REAL* x, const REAL b, REAL* y);
+/* (x, y).                          replaces fasp_blas_darray_dotprod  BlaArray.c:771 */
+REAL fasp_cuda_blas_darray_dotprod(const INT n, const REAL* x, const REAL* y);
+/* ||x||_2, ||x||_1, ||x||_inf.     replace fasp_blas_darray_norm2/_norm1/_norminf BlaArray.c:691,663,719 */
+REAL fasp_cuda_blas_darray_norm2(const INT n, const REAL* x);
+REAL fasp_cuda_blas_darray_norm1(const INT n, const REAL* x);
+REAL fasp_cuda_blas_darray_norminf(const INT n, const REAL* x);
+
 /* matrix-free operator plug-in (fasp.h:1109-1117 `mxv_matfree.fct`, shims in
  * BlaSpmvMatFree.inl:31-107): `A` is a const dCSRmat* / const dBSRmat*.                */
 void fasp_cuda_blas_mxv_csr(const void* A, const REAL* x, REAL* y);
 void fasp_cuda_blas_mxv_bsr(const void* A, const REAL* x, REAL* y);
+/* replaces fasp_solver_matfree_init  SolMatFree.c:201 for MAT_CSR (1) / MAT_BSR (2): sets mf->fct to the
+ * functions above and mf->data = A, so that FASP's own matrix-free Krylov loops (fasp_solver_pcg KryPcg.c:1260,
+ * fasp_solver_pvgmres KryPvgmres.c:1468) run their SpMV on the device.                                      */
+INT fasp_cuda_solver_matfree_init(INT matrix_format, mxv_matfree* mf, void* A);
+
+/* Dense inverse of an n x n row-major matrix (host pointers) by the blocked Gauss-Jordan kernel that factors
+ * the coarsest AMG level in place of fasp_coarse_itsolver (PreMGUtil.inl:37). ERROR_AMG_SETUP if singular. */
+INT fasp_cuda_dense_inverse(INT n, const REAL* a, REAL* ainv);
 
 /* Smoothers, same argument lists as the reference (host pointers).
  * replaces fasp_smoother_dcsr_jacobi   ItrSmootherCSR.c:98   */

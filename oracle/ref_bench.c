@@ -6,12 +6,12 @@
  * it is compiled against the reference's headers where they lie (/root/reference/base/include)
  * by oracle/build_ref.sh and linked to libfasp_omp.so.
  *
- *   fasp_ref_bench n steps warmup sample_iters
+ *   fasp_ref_bench n steps warmup [sample_iters]
  *
- * Setup runs once. One untimed FULL solve gives the reference's own iteration count; every
- * warm-up / timed step is then a bounded sample: `sample_iters` PCG iterations of that same solve
- * (fasp_solver_dcsr_pcg + fasp_precond_amg, maxit = sample_iters), scaled to a full solve by
- * iterations/sample_iters. Prints one JSON object on stdout.
+ * Setup runs once. Every warm-up / timed step is one FULL solve (fasp_solver_dcsr_pcg +
+ * fasp_precond_amg to tol 1e-8, x0 = 0): nothing is extrapolated. Only when sample_iters > 0 is given
+ * (a host too slow for full solves) is a step a bounded sample of `sample_iters` PCG iterations, scaled by
+ * (iterations+1)/(sample_iters+1), and the JSON says so. Prints one JSON object on stdout.
  *
  * NOTE (SURVEY.md finding 2): the OpenMP build of FASP ignores the requested smoother and runs
  * multicolour Gauss-Seidel, so its iteration count differs from the sequential oracle.
@@ -65,7 +65,7 @@ int main(int argc, char** argv)
     const int n       = argc > 1 ? atoi(argv[1]) : 64;
     const int steps   = argc > 2 ? atoi(argv[2]) : 3;
     const int warmup  = argc > 3 ? atoi(argv[3]) : 1;
-    int       sample  = argc > 4 ? atoi(argv[4]) : 2;
+    int       sample  = argc > 4 ? atoi(argv[4]) : 0;   /* 0 = full solves */
     int threads = 1;
 #ifdef _OPENMP
     threads = omp_get_max_threads();
@@ -106,32 +106,43 @@ int main(int argc, char** argv)
     pc.data = &pcdata;
     pc.fct  = fasp_precond_amg;
 
-    /* one full solve: the reference's own iteration count and full-solve time */
+    /* one untimed full solve: the reference's own iteration count */
     fasp_dvec_set(N, &x, 0.0);
     t0 = now();
     INT iters = fasp_solver_dcsr_pcg(&A, &b, &x, &pc, itparam.tol, itparam.abstol, itparam.maxit,
                                      itparam.stop_type, 0);
-    const double full_s = now() - t0;
+    const double first_s = now() - t0;
     if (iters <= 0) { fprintf(stderr, "reference solve failed: %d\n", iters); return 3; }
     if (sample > iters) sample = iters;
-    if (sample < 1) sample = 1;
 
-    double sum = 0.0;
+    double sum = 0.0, tmin = 1e300, tmax = 0.0;
+    const int maxit_step = sample > 0 ? sample : itparam.maxit;
     for (int k = 0; k < warmup + steps; ++k) {
         fasp_dvec_set(N, &x, 0.0);
         t0 = now();
-        fasp_solver_dcsr_pcg(&A, &b, &x, &pc, itparam.tol, itparam.abstol, sample, itparam.stop_type, 0);
+        fasp_solver_dcsr_pcg(&A, &b, &x, &pc, itparam.tol, itparam.abstol, maxit_step, itparam.stop_type, 0);
         const double dt = now() - t0;
-        if (k >= warmup) sum += dt;
+        if (k >= warmup) {
+            sum += dt;
+            if (dt < tmin) tmin = dt;
+            if (dt > tmax) tmax = dt;
+        }
     }
-    const double per_sample = steps > 0 ? sum / steps : full_s * sample / iters;
-    /* a k-iteration solve applies the preconditioner and A k+1 times (KryPcg.c:125-131) */
-    const double est_ms     = per_sample * (double)(iters + 1) / (sample + 1) * 1e3;
-    printf("{\"ms_per_solve_est\": %.3f, \"ms_full_solve_measured\": %.3f, \"iterations\": %d, "
+    double per_step = steps > 0 ? sum / steps : first_s;
+    if (steps <= 0) tmin = tmax = first_s;
+    /* sampled mode only: a k-iteration solve applies the preconditioner and A k+1 times (KryPcg.c:125-131) */
+    const double ms = (sample > 0 ? per_step * (double)(iters + 1) / (sample + 1) : per_step) * 1e3;
+    char what[256];
+    if (sample > 0)
+        snprintf(what, sizeof(what), "%d of %d PCG iterations per step, scaled by (%d+1)/(%d+1)", sample, (int)iters,
+                 (int)iters, sample);
+    else
+        snprintf(what, sizeof(what), "full solves, nothing extrapolated (%d iterations each; min %.1f max %.1f ms)",
+                 (int)iters, tmin * 1e3, tmax * 1e3);
+    printf("{\"ms_per_solve\": %.3f, \"extrapolated\": %s, \"ms_first_solve\": %.3f, \"iterations\": %d, "
            "\"levels\": %d, \"setup_s\": %.2f, \"threads\": %d, \"n\": %d, "
-           "\"sample\": \"%d of %d PCG iterations per step (OpenMP FASP, %d threads, multicolour GS), "
-           "scaled by (%d+1)/(%d+1); one untimed full solve took %.1f ms\"}\n",
-           est_ms, full_s * 1e3, (int)iters, (int)mgl[0].num_levels, setup_s, threads, n, sample,
-           (int)iters, threads, (int)iters, sample, full_s * 1e3);
+           "\"sample\": \"%s; OpenMP FASP, %d threads, multicolour GS\"}\n",
+           ms, sample > 0 ? "true" : "false", first_s * 1e3, (int)iters, (int)mgl[0].num_levels, setup_s, threads, n,
+           what, threads);
     return 0;
 }

@@ -158,9 +158,9 @@ def test_reg_gcc_golden_l1diag_amg_solver(gpu, ref, data, golden_answers):
     assert np.abs(x - data["FE_sol"]).max() < 1e-4   # regression.c:56 tolerance
 
 
-def test_pcg_with_host_callback_and_null_precond(gpu, ref, data):
-    """fasp_cuda_solver_dcsr_pcg with pc == NULL and with the reference's own host
-    fasp_precond_amg callback (KryPcg.c:128-131 plug-in contract)."""
+def test_pcg_with_null_precond(gpu, ref, data):
+    """fasp_cuda_solver_dcsr_pcg with pc == NULL (identity, KryPcg.c:128-131). The host-callback and
+    device-callback forms of the plug-in contract are in tests/test_plugins_gpu.py."""
     A, b = data["FE"], data["FE_b"]
     n = A.shape[0]
     vb, vx, vxr = T.Vec(b), T.Vec(np.zeros(n)), T.Vec(np.zeros(n))

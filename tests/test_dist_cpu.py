@@ -85,3 +85,61 @@ def test_partition_covers_rows_once():
             assert p["ia"][-1] == p["ja"].size and p["ja"].max(initial=0) < nloc + p["ghosts"].size
             assert np.all(np.diff(p["ghosts"]) > 0)
         assert np.all(seen == 1)
+
+
+SHARED_WORKER = r'''
+import os, sys, hashlib
+sys.path.insert(0, %(root)r)
+import numpy as np, torch.distributed as dist
+from faspsolver_b200 import api, problems as PB, multigpu as MG, fasp_types as T
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+hf = api.HostFasp(%(lib)r)
+A = PB.poisson7(12) if rank == 0 else None            # only rank 0 holds the global matrix
+amg = hf.amg_param(print_level=0, smoother=T.SMOOTHER_L1DIAG)
+sh = MG.SharedHierarchy(hf, A, amg, rank, world, root=%(tmp)r)
+mgl = sh.mgl
+nl = mgl[0].num_levels
+h = hashlib.sha256()
+for l in range(nl):
+    for nm in ("A", "P", "R"):
+        if nm != "A" and l == nl - 1:
+            continue
+        m = getattr(mgl[l], nm)
+        h.update(np.array([m.row, m.col, m.nnz]).tobytes())
+        h.update(np.ctypeslib.as_array(m.IA, shape=(m.row + 1,)).tobytes())
+        h.update(np.ctypeslib.as_array(m.JA, shape=(m.nnz,)).tobytes())
+        h.update(np.ctypeslib.as_array(m.val, shape=(m.nnz,)).tobytes())
+digs = [None] * world
+dist.all_gather_object(digs, (h.hexdigest(), nl, float(amg.tentative_smooth), sh.how))
+assert len(set(d[:3] for d in digs)) == 1, digs           # identical hierarchy and parameters on every rank
+assert nl >= 3 and "rank 0" in sh.how, (nl, sh.how)
+# the mapped hierarchy feeds the library's host-side slab extraction like a locally built one
+A1 = T.CSR.from_struct(mgl[1].A)
+p = MG.extract_host(A1, world, rank)
+assert p["ia"][-1] == p["ja"].size
+sh.close()
+assert rank != 0 or not os.path.exists(sh.dir)
+print("rank", rank, "ok")
+'''
+
+
+def test_shared_hierarchy_gloo(tmp_path):
+    """multigpu.SharedHierarchy: FASP's setup on rank 0 only, the other ranks map the arrays read-only."""
+    lib = ROOT / "oracle" / "_ref" / "libfasp_seq.so"
+    if not lib.exists():
+        pytest.skip("oracle/_ref/libfasp_seq.so not built")
+    world = 2
+    script = tmp_path / "worker.py"
+    script.write_text(SHARED_WORKER % {"root": str(ROOT), "lib": str(lib), "tmp": str(tmp_path)})
+    port = 29700 + (os.getpid() % 200)
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d failed:\n%s" % (r, o)
+        assert "ok" in o

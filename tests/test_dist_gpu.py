@@ -25,9 +25,24 @@ A = PB.poisson7(40); b = np.ones(A.shape[0])
 for smoother, solver_type in ((T.SMOOTHER_L1DIAG, T.SOLVER_CG), (T.SMOOTHER_JACOBI, T.SOLVER_VGMRES), (T.SMOOTHER_POLY, T.SOLVER_CG)):
     amg = hf.amg_param(print_level=0, smoother=smoother, relaxation=0.67 if smoother == T.SMOOTHER_JACOBI else 1.0)
     it = hf.its_param(itsolver_type=solver_type, tol=1e-8, maxit=200, print_level=0, restart=30)
-    mgl = hf.amg_setup(A, amg)
+    sh = MG.SharedHierarchy(hf, A if rank == 0 else None, amg, rank, world)   # setup on rank 0 only
+    mgl = sh.mgl
     s = MG.DistSolver(mgl, amg, agg_rows=2000)
-    st, x_loc = s.solve(np.ascontiguousarray(b[s.row0:s.row1]), np.zeros(s.row1 - s.row0), it)
+    nloc = s.row1 - s.row0
+    b_loc = np.ascontiguousarray(b[s.row0:s.row1])
+    st, x_loc = s.solve(b_loc, np.zeros(nloc), it)
+    st_again, x_again = s.solve(b_loc, np.zeros(nloc), it)        # cached workspace / graphs
+    assert st_again == st and np.array_equal(x_again, x_loc), (rank, st, st_again)
+    # device-pointer form with caller vectors of EXACTLY n_local entries (no ghost room, not peer-mapped):
+    # the solver must stage x itself instead of exchanging ghosts into the caller's allocation
+    d_b, d_x = L.fasp_cuda_dvec_alloc(nloc), L.fasp_cuda_dvec_alloc(nloc)
+    api.check(L.fasp_cuda_dvec_h2d(d_b, T.as_preal(b_loc), nloc))
+    api.check(L.fasp_cuda_dvec_h2d(d_x, T.as_preal(np.zeros(nloc)), nloc))
+    st_dev = s.solve_dev(d_b, d_x, it)
+    x_dev = np.empty(nloc)
+    api.check(L.fasp_cuda_dvec_d2h(T.as_preal(x_dev), d_x, nloc))
+    L.fasp_cuda_dvec_free(d_b); L.fasp_cuda_dvec_free(d_x)
+    assert st_dev == st and np.array_equal(x_dev, x_loc), (rank, st, st_dev, np.abs(x_dev - x_loc).max())
     parts = [None] * world
     dist.all_gather_object(parts, (s.row0, x_loc))
     s.close()
@@ -37,11 +52,16 @@ for smoother, solver_type in ((T.SMOOTHER_L1DIAG, T.SOLVER_CG), (T.SMOOTHER_JACO
         ref = RefFasp()
         amg_r = ref.amg_param(print_level=0, smoother=smoother, relaxation=0.67 if smoother == T.SMOOTHER_JACOBI else 1.0)
         st_ref, x_ref = ref.krylov_amg(A, b, np.zeros_like(b), it, amg_r)
+        # the one-GPU solve on the same hierarchy, while the communicator is active
+        s1 = api.KrylovAmgSolver(mgl, amg)
+        st1, x1 = s1.solve(b, np.zeros_like(b), it)
+        s1.close()
         rel = float(np.linalg.norm(b - A.to_scipy() @ x) / np.linalg.norm(b))
         dx = float(np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref))
-        print("RESULT", json.dumps({"smoother": smoother, "st": st, "st_ref": st_ref, "rel": rel, "dx": dx}))
-    hf.amg_free(mgl, amg)
+        dx1 = float(np.linalg.norm(x - x1) / np.linalg.norm(x1))
+        print("RESULT", json.dumps({"smoother": smoother, "st": st, "st_ref": st_ref, "st1": st1, "rel": rel, "dx": dx, "dx1": dx1}))
     MG.barrier()
+    sh.close()
 L.fasp_cuda_comm_finalize()
 '''
 
@@ -67,3 +87,4 @@ def test_two_rank_solve_matches_reference(tmp_path):
     for d in res:
         assert d["st"] > 0 and abs(d["st"] - d["st_ref"]) <= 1, d
         assert d["rel"] <= 1e-8 * 1.001 and d["dx"] <= 1e-8, d
+        assert abs(d["st"] - d["st1"]) <= 1 and d["dx1"] <= 1e-8, d

@@ -26,9 +26,24 @@ def test_unsupported_smoother_and_solver_codes(gpu, ref, data):
     it2 = ref.its_param(itsolver_type=2, tol=1e-8, maxit=100, print_level=0)   # BiCGstab: not on the path
     st, _ = api.fasp_cuda_solver_dcsr_krylov_amg(A, b, np.zeros_like(b), it2, amg)
     assert st == T.ERROR_SOLVER_TYPE
-    it3 = ref.its_param(itsolver_type=T.SOLVER_CG, tol=1e-8, maxit=100, print_level=0, stop_type=T.STOP_REL_PRECRES)
+    it3 = ref.its_param(itsolver_type=T.SOLVER_CG, tol=1e-8, maxit=100, print_level=0, stop_type=7)   # no such type
     st, _ = api.fasp_cuda_solver_dcsr_krylov_amg(A, b, np.zeros_like(b), it3, amg)
     assert st == T.ERROR_INPUT_PAR
+    it4 = ref.its_param(itsolver_type=T.SOLVER_GMRES, tol=1e-8, maxit=100, print_level=0, stop_type=7)
+    st, _ = api.fasp_cuda_solver_dcsr_krylov_amg(A, b, np.zeros_like(b), it4, amg)
+    assert st == T.ERROR_INPUT_PAR
+    # a BSR coarsest level beyond coarse_dense_max has no iterative fallback: loud error, not a wrong answer
+    Ab, bb = PB.blockoil7(6)
+    gpu.fasp_cuda_set_option(b"coarse_dense_max", 16.0)
+    try:
+        vb, vx = T.Vec(bb), T.Vec(np.zeros_like(bb))
+        itb = ref.its_param(itsolver_type=T.SOLVER_VGMRES, tol=1e-8, maxit=100, print_level=0)
+        amgb = ref.amg_param(print_level=0, AMG_type=T.UA_AMG, aggregation_type=T.VMB, smoother=T.SMOOTHER_JACOBI,
+                             coarse_dof=100)
+        st = gpu.fasp_cuda_solver_dbsr_krylov_amg(Ab.ptr(), vb.ptr(), vx.ptr(), C.byref(itb), C.byref(amgb))
+    finally:
+        gpu.fasp_cuda_set_option(b"coarse_dense_max", 8192.0)
+    assert st == T.ERROR_AMG_SETUP, st
 
 
 def test_gs_as_multicolor_option(gpu, ref, data):
@@ -87,30 +102,39 @@ z = np.load(%r)
 A = T.CSR(z["FE_ia"].size - 1, z["FE_ia"].size - 1, z["FE_ia"], z["FE_ja"], z["FE_val"]); b = z["FE_b"]
 ref = RefFasp()
 which = sys.argv[1]
-it = ref.its_param(itsolver_type=T.SOLVER_CG, tol=1e-8, maxit=100, print_level=2)
+kind = int(sys.argv[2])
+x0 = np.zeros_like(b)
+if kind in (1, 3):     # zero right-hand side: FASP jumps to FINISHED before the iteration table (KryPcg.c:156)
+    b = np.zeros_like(b)
+it = ref.its_param(itsolver_type=(T.SOLVER_CG, T.SOLVER_CG, T.SOLVER_VGMRES, T.SOLVER_VGMRES)[kind], tol=1e-8,
+                   maxit=100, print_level=2)
 amg = ref.amg_param(print_level=0, smoother=T.SMOOTHER_L1DIAG)
 if which == "gpu":
     L = api.lib(); L.fasp_cuda_init(0)
-    st, x = api.fasp_cuda_solver_dcsr_krylov_amg(A, b, np.zeros_like(b), it, amg)
+    st, x = api.fasp_cuda_solver_dcsr_krylov_amg(A, b, x0, it, amg)
 else:
-    st, x = ref.krylov_amg(A, b, np.zeros_like(b), it, amg)
+    st, x = ref.krylov_amg(A, b, x0, it, amg)
 sys.stdout.flush()
 ''' % (str(ROOT), str(ROOT / "tests" / "golden" / "fasp_data.npz"))
-    outs = {}
-    for which in ("gpu", "ref"):
-        r = subprocess.run([sys.executable, "-c", code, which], capture_output=True, text=True, cwd=str(ROOT))
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs[which] = [l for l in r.stdout.splitlines() if "|" in l or l.startswith("Number of iterations") or l.startswith("---")]
-    assert len(outs["gpu"]) == len(outs["ref"]) > 8
-    for lg, lr in zip(outs["gpu"], outs["ref"]):
-        if lg == lr:
-            continue
-        # same layout; numbers may differ in the last printed digit (reduction order)
-        fg, fr = lg.replace("|", " ").split(), lr.replace("|", " ").split()
-        assert len(fg) == len(fr) and len(lg) == len(lr), (lg, lr)
-        for a, b_ in zip(fg, fr):
-            a, b_ = a.rstrip("."), b_.rstrip(".")
-            try:
-                assert abs(float(a) - float(b_)) <= 2e-6 * max(abs(float(b_)), 1e-300) + 1.01e-4, (lg, lr)
-            except ValueError:
-                assert a == b_, (lg, lr)
+    for kind in (0, 1, 2, 3):
+        outs = {}
+        for which in ("gpu", "ref"):
+            r = subprocess.run([sys.executable, "-c", code, which, str(kind)], capture_output=True, text=True,
+                               cwd=str(ROOT))
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs[which] = [l for l in r.stdout.splitlines()
+                           if "|" in l or l.startswith("Number of iterations") or l.startswith("---")]
+        assert len(outs["gpu"]) == len(outs["ref"]), (kind, outs)
+        assert len(outs["gpu"]) > (8 if kind in (0, 2) else 0), (kind, outs)
+        for lg, lr in zip(outs["gpu"], outs["ref"]):
+            if lg == lr:
+                continue
+            # same layout; numbers may differ in the last printed digit (reduction order)
+            fg, fr = lg.replace("|", " ").split(), lr.replace("|", " ").split()
+            assert len(fg) == len(fr) and len(lg) == len(lr), (lg, lr)
+            for a, b_ in zip(fg, fr):
+                a, b_ = a.rstrip("."), b_.rstrip(".")
+                try:
+                    assert abs(float(a) - float(b_)) <= 2e-6 * max(abs(float(b_)), 1e-300) + 1.01e-4, (lg, lr)
+                except ValueError:
+                    assert a == b_, (lg, lr)
