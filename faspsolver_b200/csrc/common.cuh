@@ -69,8 +69,11 @@ struct Options {
     int    vec_lpr          = 0;   // > 0: force this many lanes per row in the vector kernel
     int    gs_multicolor    = 0;   // accept SMOOTHER_GS in the cycle as multicolour GS (OpenMP-FASP semantics)
     int    profile          = 0;   // record CUDA events around every matrix kernel (no graphs)
-    int    bsr_rb           = 32;  // BSR pipelined kernel: block rows per CTA (32 / 64), nb <= 4
-    int    bsr_u            = 4;   // its blocks in flight per thread (4 / 8), nb <= 4
+    int    overlap          = 1;   // multi-GPU: rows without ghost columns run on a second stream while the ghosts travel
+    int    overlap_min_rows = 256; // ... when the operator's interior has at least this many rows
+    int    bsr_rb           = 64;  // BSR pipelined kernel: block rows per CTA (32 / 64), nb <= 4. Measured on the 3x3-block
+                                   // 7-point matrix (160^3): 32/4 0.69 of the copy peak, 32/8 0.76, 64/4 0.78, 64/8 0.81-0.85
+    int    bsr_u            = 8;   // its blocks in flight per thread (4 / 8), nb <= 4
     int    bsr_stages       = 2;   // its shared-memory stages per CTA (2..4)
 };
 
@@ -80,6 +83,9 @@ struct Ctx {
     int          sm_count = 148;
     size_t       l2_bytes = 126u << 20;
     cudaStream_t stream   = nullptr;
+    cudaStream_t side     = nullptr;    // second stream: interior rows of a partitioned operator (overlap with the exchange)
+    cudaStream_t launch_stream = nullptr;   // where FC_LAUNCH puts kernels: `stream`, or `side` inside a fork
+    cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
     long long    launches = 0;
     bool         capturing = false;     // inside a stream capture: launches counted per replay
     long long    captured  = 0;
@@ -89,6 +95,11 @@ struct Ctx {
     double*       red_partials = nullptr;
     size_t        red_cap      = 0;
     unsigned int* red_ticket   = nullptr;
+    // the same for kernels on the side stream (they may run concurrently with a reducing kernel on `stream`)
+    double*       red_partials_side = nullptr;
+    size_t        red_cap_side      = 0;
+    unsigned int* red_ticket_side   = nullptr;
+    double*       side_tot          = nullptr;   // totals of a side-stream reduction, added by the main-stream kernel
     // per-launch profile records (opt.profile): tag, events, algorithmic bytes
     struct ProfRec {
         cudaEvent_t e0, e1;
@@ -107,7 +118,7 @@ void ensure_init();
 #define FC_LAUNCH(kernel, grid, block, smem, ...)                                          \
     do {                                                                                   \
         ::fc::Ctx& c__ = ::fc::ctx();                                                      \
-        kernel<<<(grid), (block), (smem), c__.stream>>>(__VA_ARGS__);                      \
+        kernel<<<(grid), (block), (smem), c__.launch_stream>>>(__VA_ARGS__);               \
         if (c__.capturing) c__.captured++; else c__.launches++;                            \
         FC_CUDA(cudaPeekAtLastError());                                                    \
     } while (0)
@@ -156,14 +167,17 @@ struct DevCSR {
     double*   dinv = nullptr;     // 1/diag (first stored diagonal entry), poly smoother
     size_t    bytes = 0;
     bool      dup_diag = false;   // some row stores more than one (i,i) entry
+    // multi-GPU: the longest run of rows (and of whole row blocks) without ghost columns; empty = no split
+    int       int_row0 = 0, int_row1 = 0, int_blk0 = 0, int_blk1 = 0;
     int       vec_cap = 0;        // multi-GPU: entries a gathered vector holds (uniform over the ranks)
     int       nghost = 0;         // multi-GPU: ghost entries behind the owned part of a gathered vector
     HaloPlan* halo = nullptr;     // multi-GPU: ghosts of the gathered vector are exchanged before the kernel
 };
 
 // Upload a host CSR (FASP layout). `pattern_only` drops the values (UA-AMG P/R: all ones).
+// ghost_col0 >= 0 (multi-GPU slabs): columns >= ghost_col0 are ghosts; the interior row / block range is recorded.
 void csr_upload(DevCSR& d, int rows, int cols, long long nnz, const int* ia, const int* ja,
-                const double* val, bool pattern_only = false);
+                const double* val, bool pattern_only = false, int ghost_col0 = -1);
 void csr_free(DevCSR& d);
 // lazily built smoother side data
 void csr_ensure_diag(DevCSR& d);   // diag + dpos (+ dup_diag)
@@ -223,6 +237,7 @@ struct CsrArgs {
     double*       u_acc  = nullptr; // POLYJ (last step): u += vnew
     double        k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0;
     Reduce        red;
+    const double* red_add = nullptr;     // totals of the other part of a split launch, added in the finalize step
     const int*    done = nullptr;
     bool          conditional = false;   // launch gated by a rarely-taken branch flag (profiling tag)
 };

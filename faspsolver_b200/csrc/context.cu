@@ -51,8 +51,16 @@ void ensure_init()
     c.sm_count = p.multiProcessorCount;
     c.l2_bytes = (size_t)p.l2CacheSize;
     FC_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    FC_CUDA(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+    c.launch_stream = c.stream;
+    FC_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+    FC_CUDA(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     c.red_ticket = dalloc<unsigned int>((size_t)1 << 20);   // [0] groups done, [1+g] arrivals in group g
     FC_CUDA(cudaMemset(c.red_ticket, 0, sizeof(unsigned int) << 20));
+    c.red_ticket_side = dalloc<unsigned int>((size_t)1 << 16);
+    FC_CUDA(cudaMemset(c.red_ticket_side, 0, sizeof(unsigned int) << 16));
+    c.side_tot = dalloc<double>(4);
+    FC_CUDA(cudaMemset(c.side_tot, 0, 4 * sizeof(double)));
     c.inited = true;
     if (const char* s = getenv("FASP_CUDA_STRICT")) c.opt.strict = atoi(s);
     if (const char* s = getenv("FASP_CUDA_GRAPH")) c.opt.graph = atoi(s);
@@ -101,19 +109,26 @@ double* red_partials(size_t nblocks)
 {
     Ctx&   c    = ctx();
     size_t need = 4 * (nblocks + nblocks / 256 + 2) + 16;   // up to 4 sums per CTA + per group
-    if (nblocks / 256 + 2 > ((size_t)1 << 20)) fail(ERROR_MAT_SIZE, "grid too large for the reduction tickets");
-    if (need > c.red_cap) {
+    const bool side = (c.launch_stream == c.side) && c.side != nullptr;
+    if (nblocks / 256 + 2 > ((size_t)1 << (side ? 16 : 20))) fail(ERROR_MAT_SIZE, "grid too large for the reduction tickets");
+    double*& buf = side ? c.red_partials_side : c.red_partials;
+    size_t&  cap = side ? c.red_cap_side : c.red_cap;
+    if (need > cap) {
         if (c.capturing)
             fail(ERROR_SOLVER_MISC, "reduction scratch must be reserved before graph capture");
-        size_t cap = c.red_cap ? c.red_cap : (size_t)1 << 16;
-        while (cap < need) cap *= 2;
-        c.red_partials = dalloc<double>(cap);   // old buffer intentionally kept
-        c.red_cap      = cap;
+        size_t ncap = cap ? cap : (size_t)1 << 16;
+        while (ncap < need) ncap *= 2;
+        buf = dalloc<double>(ncap);   // old buffer intentionally kept
+        cap = ncap;
     }
-    return c.red_partials;
+    return buf;
 }
 
-unsigned int* red_ticket() { return ctx().red_ticket; }
+unsigned int* red_ticket()
+{
+    Ctx& c = ctx();
+    return (c.launch_stream == c.side && c.side != nullptr) ? c.red_ticket_side : c.red_ticket;
+}
 
 __global__ void flush_kernel(char* buf, size_t n, char v)
 {

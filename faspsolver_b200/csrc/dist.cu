@@ -192,8 +192,9 @@ static HaloPlan* upload_part(DevCSR& d, const dCSRmat& A, const std::vector<int>
 {
     LocalCSR loc;
     dist_extract(A, roff[rank], roff[rank + 1], coff, rank, pattern, loc);
+    const int nloc_cols = coff.empty() ? -1 : coff[rank + 1] - coff[rank];   // columns behind it are ghosts
     csr_upload(d, loc.rows, loc.cols, (long long)loc.ja.size(), loc.ia.data(), loc.ja.data(),
-               loc.val.empty() ? nullptr : loc.val.data(), pattern);
+               loc.val.empty() ? nullptr : loc.val.data(), pattern, nloc_cols);
     if (coff.empty()) return nullptr;
     HaloPlan* h = make_plan(A, roff, coff, loc, rank);
     d.halo      = h;

@@ -344,6 +344,10 @@ void GmresCache::release()
     t0 = t1 = nullptr;
     if (pin_h) cudaFreeHost(pin_h);
     pin_h = nullptr;
+    if (pin_flags) cudaFreeHost(pin_flags);
+    pin_flags = nullptr;
+    for (auto& e : ev) cudaEventDestroy(e);
+    ev.clear();
     dfree(pin_d);
     pin_d = nullptr;
     if (registered && work) p2p_unregister(work);
@@ -382,8 +386,13 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
     // basis p[0..R], w, r, (flexible: z[0..R-1]) ; hh (R+1) x R, c, s, rs ; norms + absres history
     const size_t nsmall = (size_t)(R + 1) * R + 2 * (size_t)R + (R + 1) + 2 * (size_t)hcap;
     const size_t nvec   = (size_t)(R + 3) + (flexible ? (size_t)R : 0);
-    if (W.n != n || W.ldp != ldp || W.R != R || W.hcap != hcap || W.kind != kind) {
+    const int look = c.opt.lookahead < 1 ? 1 : c.opt.lookahead;
+    if (W.n != n || W.ldp != ldp || W.R != R || W.hcap != hcap || W.kind != kind || W.look != look) {
         W.release();
+        W.look = look;
+        FC_CUDA(cudaMallocHost(&W.pin_flags, sizeof(int) * (look + 1)));
+        W.ev.resize(look + 1);
+        for (auto& e : W.ev) FC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         W.work = dalloc<double>(nvec * ldp + nsmall);
         if (p2p_active() && A.distributed()) {   // basis vectors are gathered by the peers' kernels
             p2p_register(W.work, sizeof(double) * (nvec * ldp + nsmall));
@@ -545,7 +554,23 @@ int gmres_solve(LinOp& A, const double* b, double* x, Prec& pc, double tol, doub
             start_graph.run(use_graph, cycle_start);
             int steps = Restart;
             if (steps > MaxIt - iter) steps = MaxIt - iter;
-            for (int i = 1; i <= steps; ++i) step_graph[i].run(use_graph, [&]() { inner_step(i); });
+            // Inner steps are enqueued `look` ahead of an asynchronous read of the device's skip_inner flag: once
+            // the restart cycle has met its exit test (KryPvgmres.c:263) the remaining steps would all return at
+            // once, so they are not launched at all (a converged 11-iteration GMRES(30) solve used to enqueue 19
+            // gated V-cycles, ~200 empty kernels each).
+            bool exited = false;
+            for (int i = 1; i <= steps && !exited; ++i) {
+                step_graph[i].run(use_graph, [&]() { inner_step(i); });
+                const int slot = i % (look + 1);
+                FC_CUDA(cudaMemcpyAsync(&W.pin_flags[slot], &st->skip_inner, sizeof(int), cudaMemcpyDeviceToHost,
+                                        c.stream));
+                FC_CUDA(cudaEventRecord(W.ev[slot], c.stream));
+                if (i > look) {
+                    const int old = (i - look) % (look + 1);
+                    FC_CUDA(cudaEventSynchronize(W.ev[old]));
+                    if (W.pin_flags[old]) exited = true;
+                }
+            }
             end_graph.run(use_graph, cycle_end);
             FC_CUDA(cudaMemcpyAsync(pin_h, pin_d, sizeof(GmPinned), cudaMemcpyDeviceToHost, c.stream));
             FC_CUDA(cudaStreamSynchronize(c.stream));

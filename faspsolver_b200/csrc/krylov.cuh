@@ -146,6 +146,9 @@ struct GmresCache {
     double* work = nullptr;
     void*   st   = nullptr;
     void *  pin_d = nullptr, *pin_h = nullptr;
+    int*    pin_flags = nullptr;          // pinned ring of skip_inner flags read `look` steps behind the launches
+    std::vector<cudaEvent_t> ev;
+    int     look = 0;
     size_t  n = 0, ldp = 0;
     int     R = 0, hcap = 0, kind = -1;
     bool    registered = false;

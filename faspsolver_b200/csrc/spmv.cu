@@ -29,6 +29,14 @@ namespace fc {
 constexpr int TPB     = 256;
 constexpr int CAP_MAX = 2048;   // largest row-block capacity (products per CTA)
 
+// A launch covers the logical units j = 0 .. count-1 (row blocks of the pipelined kernel, rows of the others);
+// unit j is lo + j, plus `jump` once j >= split: one contiguous range (the interior of a multi-GPU slab) or two
+// (the boundary rows at both ends of the slab), without a second launch.
+struct UnitRange {
+    int lo, split, jump, count;
+    __host__ __device__ __forceinline__ long long map(long long j) const { return lo + j + (j >= split ? jump : 0); }
+};
+
 struct CsrView {
     const int*    ia;
     const int*    ja;
@@ -145,9 +153,10 @@ struct PipeMeta {
 
 template <int MODE, bool PATTERN, int T, int UG>
 __global__ void __launch_bounds__(T)
-csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nstages,
+csr_pipe_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, const int nstages,
                 const int strict, double* partials, unsigned int* ticket)
 {
+    const int nblk = ur.count;   // logical row blocks of this launch
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ __align__(8) unsigned long long s_bar[P_MAX_STAGES];
     __shared__ PipeMeta s_meta[P_MAX_STAGES];
@@ -192,7 +201,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (int s = 0; s < nstages; ++s) {
             const long long blk = (long long)blockIdx.x + (long long)s * G;
-            if (blk < nblk) issue((int)blk, s);
+            if (blk < nblk) issue((int)ur.map(blk), s);
         }
     }
     __syncthreads();
@@ -328,7 +337,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
             const long long refill = blk + (long long)nstages * G;
             if (refill < nblk) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue((int)refill, s);
+                issue((int)ur.map(refill), s);
             }
         }
         if (++s == nstages) s = 0, ph ^= 1;
@@ -337,8 +346,8 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
     if (want_dot || want_n2) {
         double v[2] = {red_dot, red_n2};
         grid_reduce<2, 0>(v, partials, ticket, [&](const double* t) {
-            if (want_dot) *a.red.dot_out = t[0];
-            if (want_n2) *a.red.nrm2_out = t[1];
+            if (want_dot) *a.red.dot_out = t[0] + (a.red_add ? a.red_add[0] : 0.0);
+            if (want_n2) *a.red.nrm2_out = t[1] + (a.red_add ? a.red_add[1] : 0.0);
         });
     }
 }
@@ -351,15 +360,15 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const int nblk, const int nsta
 // ------------------------------------------------------------------------------------
 template <int MODE, bool PATTERN, int LPR>
 __global__ void __launch_bounds__(TPB)
-csr_vector_kernel(const CsrView A, const CsrArgs a, const int nrows, double* partials,
+csr_vector_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, double* partials,
                   unsigned int* ticket)
 {
     if (a.done != nullptr && *a.done != 0) return;
     const long long gt   = (long long)blockIdx.x * TPB + threadIdx.x;
     const int       lane = (int)(gt & (LPR - 1));
     const long long rowl = gt / LPR;
-    const bool      valid = rowl < nrows;
-    const int       row   = valid ? (int)rowl : 0;
+    const bool      valid = rowl < ur.count;
+    const int       row   = valid ? (int)ur.map(rowl) : 0;
     const double* __restrict__ x   = a.x;
     const int*    __restrict__ ja  = A.ja;
     const double* __restrict__ val = A.val;
@@ -406,8 +415,8 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const int nrows, double* par
     if (want_dot || want_n2) {
         double v[2] = {red_dot, red_n2};
         grid_reduce<2, 0>(v, partials, ticket, [&](const double* t) {
-            if (want_dot) *a.red.dot_out = t[0];
-            if (want_n2) *a.red.nrm2_out = t[1];
+            if (want_dot) *a.red.dot_out = t[0] + (a.red_add ? a.red_add[0] : 0.0);
+            if (want_n2) *a.red.nrm2_out = t[1] + (a.red_add ? a.red_add[1] : 0.0);
         });
     }
 }
@@ -421,7 +430,7 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const int nrows, double* par
 // ------------------------------------------------------------------------------------
 template <int MODE, bool PATTERN, int WPR>
 __global__ void __launch_bounds__(TPB)
-csr_wide_kernel(const CsrView A, const CsrArgs a, const int nrows, double* partials, unsigned int* ticket)
+csr_wide_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, double* partials, unsigned int* ticket)
 {
     constexpr int NW  = TPB / 32;
     constexpr int RPC = NW / WPR;   // rows per CTA
@@ -430,8 +439,8 @@ csr_wide_kernel(const CsrView A, const CsrArgs a, const int nrows, double* parti
     const int       warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int       rl   = warp / WPR, wl = warp - rl * WPR;
     const long long rowl = (long long)blockIdx.x * RPC + rl;
-    const bool      valid = rowl < nrows;
-    const int       row   = valid ? (int)rowl : 0;
+    const bool      valid = rowl < ur.count;
+    const int       row   = valid ? (int)ur.map(rowl) : 0;
     const double* __restrict__ x   = a.x;
     const int*    __restrict__ ja  = A.ja;
     const double* __restrict__ val = A.val;
@@ -481,30 +490,30 @@ csr_wide_kernel(const CsrView A, const CsrArgs a, const int nrows, double* parti
     if (want_dot || want_n2) {
         double v[2] = {red_dot, red_n2};
         grid_reduce<2, 0>(v, partials, ticket, [&](const double* t) {
-            if (want_dot) *a.red.dot_out = t[0];
-            if (want_n2) *a.red.nrm2_out = t[1];
+            if (want_dot) *a.red.dot_out = t[0] + (a.red_add ? a.red_add[0] : 0.0);
+            if (want_n2) *a.red.nrm2_out = t[1] + (a.red_add ? a.red_add[1] : 0.0);
         });
     }
 }
 
 template <int MODE, bool PATTERN, int WPR>
-static void launch_wide(const DevCSR& A, const CsrView& v, const CsrArgs& a)
+static void launch_wide(const DevCSR& A, const CsrView& v, const CsrArgs& a, const UnitRange& ur)
 {
     constexpr int RPC  = (TPB / 32) / WPR;
-    const int     grid = (A.rows + RPC - 1) / RPC;
+    const int     grid = (ur.count + RPC - 1) / RPC;
     double*       part = nullptr;
     unsigned int* tick = nullptr;
     if (a.red.dot_out || a.red.nrm2_out) {
         part = red_partials((size_t)grid);
         tick = red_ticket();
     }
-    FC_LAUNCH((csr_wide_kernel<MODE, PATTERN, WPR>), grid, TPB, 0, v, a, A.rows, part, tick);
+    FC_LAUNCH((csr_wide_kernel<MODE, PATTERN, WPR>), grid, TPB, 0, v, a, ur, part, tick);
 }
 
 template <int MODE, bool PATTERN, int LPR>
-static void launch_vector(const DevCSR& A, const CsrView& v, const CsrArgs& a)
+static void launch_vector(const DevCSR& A, const CsrView& v, const CsrArgs& a, const UnitRange& ur)
 {
-    const long long threads = (long long)A.rows * LPR;
+    const long long threads = (long long)ur.count * LPR;
     const int       grid    = (int)((threads + TPB - 1) / TPB);
     double*         part    = nullptr;
     unsigned int*   tick    = nullptr;
@@ -512,12 +521,12 @@ static void launch_vector(const DevCSR& A, const CsrView& v, const CsrArgs& a)
         part = red_partials((size_t)grid);
         tick = red_ticket();
     }
-    FC_LAUNCH((csr_vector_kernel<MODE, PATTERN, LPR>), grid, TPB, 0, v, a, A.rows, part, tick);
+    FC_LAUNCH((csr_vector_kernel<MODE, PATTERN, LPR>), grid, TPB, 0, v, a, ur, part, tick);
 }
 
 // persistent grid: as many CTAs per SM as the stage rings allow
 template <int MODE, bool PATTERN, int T, int UG = 8>
-static void launch_pipe(const DevCSR& A, const CsrView& v, const CsrArgs& a, double* part,
+static void launch_pipe(const DevCSR& A, const CsrView& v, const CsrArgs& a, const UnitRange& ur, double* part,
                         unsigned int* tick)
 {
     Ctx&         c     = ctx();
@@ -537,53 +546,77 @@ static void launch_pipe(const DevCSR& A, const CsrView& v, const CsrArgs& a, dou
     if (per_sm > c.opt.pipe_ctas) per_sm = c.opt.pipe_ctas;
     if (per_sm > 2048 / T) per_sm = 2048 / T;
     long long grid = (long long)c.sm_count * per_sm;
-    if (grid > A.nblk) grid = A.nblk;
-    FC_LAUNCH((csr_pipe_kernel<MODE, PATTERN, T, UG>), (int)grid, T, smem, v, a, A.nblk, nst,
+    if (grid > ur.count) grid = ur.count;
+    FC_LAUNCH((csr_pipe_kernel<MODE, PATTERN, T, UG>), (int)grid, T, smem, v, a, ur, nst,
               c.opt.strict, part, tick);
 }
 
+// which: 0 all rows, 1 interior rows only (no ghost columns), 2 the rows around the interior
 template <int MODE, bool PATTERN>
-static void launch_pattern(const DevCSR& A, const CsrView& v, const CsrArgs& a)
+static void launch_pattern(const DevCSR& A, const CsrView& v, const CsrArgs& a, int which)
 {
     Ctx& c = ctx();
     if (A.vec_lpr > 0 && !c.opt.strict) {
+        UnitRange ur{0, A.rows, 0, A.rows};
+        if (which == 1) ur = UnitRange{A.int_row0, A.int_row1 - A.int_row0, 0, A.int_row1 - A.int_row0};
+        if (which == 2) ur = UnitRange{0, A.int_row0, A.int_row1 - A.int_row0, A.rows - (A.int_row1 - A.int_row0)};
+        if (ur.count <= 0) return;
         switch (A.vec_lpr) {
-            case 4: launch_vector<MODE, PATTERN, 4>(A, v, a); return;
-            case 8: launch_vector<MODE, PATTERN, 8>(A, v, a); return;
-            case 16: launch_vector<MODE, PATTERN, 16>(A, v, a); return;
-            case 64: launch_wide<MODE, PATTERN, 2>(A, v, a); return;
-            case 128: launch_wide<MODE, PATTERN, 4>(A, v, a); return;
-            case 256: launch_wide<MODE, PATTERN, 8>(A, v, a); return;
-            default: launch_vector<MODE, PATTERN, 32>(A, v, a); return;
+            case 4: launch_vector<MODE, PATTERN, 4>(A, v, a, ur); return;
+            case 8: launch_vector<MODE, PATTERN, 8>(A, v, a, ur); return;
+            case 16: launch_vector<MODE, PATTERN, 16>(A, v, a, ur); return;
+            case 64: launch_wide<MODE, PATTERN, 2>(A, v, a, ur); return;
+            case 128: launch_wide<MODE, PATTERN, 4>(A, v, a, ur); return;
+            case 256: launch_wide<MODE, PATTERN, 8>(A, v, a, ur); return;
+            default: launch_vector<MODE, PATTERN, 32>(A, v, a, ur); return;
         }
     }
+    UnitRange ur{0, A.nblk, 0, A.nblk};
+    if (which == 1) ur = UnitRange{A.int_blk0, A.int_blk1 - A.int_blk0, 0, A.int_blk1 - A.int_blk0};
+    if (which == 2) ur = UnitRange{0, A.int_blk0, A.int_blk1 - A.int_blk0, A.nblk - (A.int_blk1 - A.int_blk0)};
+    if (ur.count <= 0) return;
     double*       part = nullptr;
     unsigned int* tick = nullptr;
     if (a.red.dot_out || a.red.nrm2_out) {
-        part = red_partials((size_t)A.nblk);
+        part = red_partials((size_t)ur.count);
         tick = red_ticket();
     }
     switch (A.blk_tpb) {
-        case 64: launch_pipe<MODE, PATTERN, 64>(A, v, a, part, tick); return;
+        case 64: launch_pipe<MODE, PATTERN, 64>(A, v, a, ur, part, tick); return;
         case 128:
             // rows of 6+ entries: 16 gathers in flight per row thread (one round for a 7-point row, two
             // for the 19-entry rows of the first coarse level instead of three) at 64 registers, still
             // 8 CTAs per SM; measured +4 % (level 0) and +10 % (level 1) over the 8-deep variant, which
             // the short rows of the transfer operators keep
             if (c.opt.gather16_min_avg > 0 && A.rows > 0 && (double)A.nnz >= (double)c.opt.gather16_min_avg * A.rows)
-                launch_pipe<MODE, PATTERN, 128, 16>(A, v, a, part, tick);
+                launch_pipe<MODE, PATTERN, 128, 16>(A, v, a, ur, part, tick);
             else
-                launch_pipe<MODE, PATTERN, 128>(A, v, a, part, tick);
+                launch_pipe<MODE, PATTERN, 128>(A, v, a, ur, part, tick);
             return;
-        default: launch_pipe<MODE, PATTERN, 256>(A, v, a, part, tick); return;
+        default: launch_pipe<MODE, PATTERN, 256>(A, v, a, ur, part, tick); return;
     }
 }
 
 template <int MODE>
-static void launch_mode(const DevCSR& A, const CsrView& v, const CsrArgs& a)
+static void launch_mode(const DevCSR& A, const CsrView& v, const CsrArgs& a, int which)
 {
-    if (A.val == nullptr) launch_pattern<MODE, true>(A, v, a);
-    else launch_pattern<MODE, false>(A, v, a);
+    if (A.val == nullptr) launch_pattern<MODE, true>(A, v, a, which);
+    else launch_pattern<MODE, false>(A, v, a, which);
+}
+
+static void launch_any(const DevCSR& A, const CsrView& v, const CsrArgs& a, int which)
+{
+    switch (a.mode) {
+        case CSR_MXV: launch_mode<CSR_MXV>(A, v, a, which); break;
+        case CSR_AXPY: launch_mode<CSR_AXPY>(A, v, a, which); break;
+        case CSR_RESID: launch_mode<CSR_RESID>(A, v, a, which); break;
+        case CSR_JACOBI: launch_mode<CSR_JACOBI>(A, v, a, which); break;
+        case CSR_L1: launch_mode<CSR_L1>(A, v, a, which); break;
+        case CSR_POLY1: launch_mode<CSR_POLY1>(A, v, a, which); break;
+        case CSR_POLYJ: launch_mode<CSR_POLYJ>(A, v, a, which); break;
+        case CSR_RESID_DINV: launch_mode<CSR_RESID_DINV>(A, v, a, which); break;
+        default: fail(ERROR_INPUT_PAR, "csr_launch: unknown mode %d", a.mode);
+    }
 }
 
 void csr_launch(const DevCSR& A, const CsrArgs& a_in)
@@ -594,32 +627,65 @@ void csr_launch(const DevCSR& A, const CsrArgs& a_in)
         vec_reduce(a_in.y, 0, a_in.red, a_in.done);   // zero contribution (+ the all-reduce)
         return;
     }
+    Ctx&       c       = ctx();
     const bool reads_y = (a_in.mode == CSR_AXPY || a_in.mode == CSR_RESID || a_in.mode >= CSR_JACOBI);
     double     pbytes  = csr_spmv_bytes(A, reads_y);
     if (a_in.mode == CSR_JACOBI || a_in.mode == CSR_L1) pbytes += 16.0 * A.rows;   // + u read, d read
     if (a_in.mode >= CSR_POLY1) pbytes += 16.0 * A.rows;
     const CsrArgs& a = a_in;
-    if (A.halo) halo_exchange(*A.halo, const_cast<double*>(a.x), a.done, a.conditional);
-    ProfScope  prof(a.conditional ? a.mode + 50 : a.mode, A.rows, A.nnz, pbytes);
-    CsrView v{A.ia, A.ja, A.val, A.rowblk, A.blkdesc, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap, ctx().opt.rowwise_max};
     switch (a.mode) {
-        case CSR_MXV: launch_mode<CSR_MXV>(A, v, a); break;
-        case CSR_AXPY: launch_mode<CSR_AXPY>(A, v, a); break;
-        case CSR_RESID: launch_mode<CSR_RESID>(A, v, a); break;
         case CSR_JACOBI:
             if (!A.diag) fail(ERROR_DATA_STRUCTURE, "Jacobi sweep without diagonal data");
-            if (A.dup_diag)
-                fail(ERROR_DATA_STRUCTURE, "Jacobi sweep: a row stores several diagonal entries");
-            launch_mode<CSR_JACOBI>(A, v, a);
+            if (A.dup_diag) fail(ERROR_DATA_STRUCTURE, "Jacobi sweep: a row stores several diagonal entries");
             break;
         case CSR_L1:
             if (!A.l1) fail(ERROR_DATA_STRUCTURE, "L1 sweep without l1 row sums");
-            launch_mode<CSR_L1>(A, v, a);
             break;
-        case CSR_POLY1: launch_mode<CSR_POLY1>(A, v, a); break;
-        case CSR_POLYJ: launch_mode<CSR_POLYJ>(A, v, a); break;
-        case CSR_RESID_DINV: launch_mode<CSR_RESID_DINV>(A, v, a); break;
-        default: fail(ERROR_INPUT_PAR, "csr_launch: unknown mode %d", a.mode);
+        default: break;
+    }
+    CsrView v{A.ia, A.ja, A.val, A.rowblk, A.blkdesc, A.diag, A.dpos, A.l1, A.dinv, A.blk_cap, c.opt.rowwise_max};
+    // Multi-GPU: the rows of the slab that touch no ghost column (its interior: all but the planes next to the
+    // neighbours) start on a second stream at once, the ghost exchange (push over NVLink + flag barrier) runs
+    // beside them, and only the boundary rows wait for it. In a captured graph this is a fork / join.
+    const bool use_vec = A.vec_lpr > 0 && !c.opt.strict;
+    const int  n_int   = use_vec ? A.int_row1 - A.int_row0 : A.int_blk1 - A.int_blk0;
+    const int  n_bnd   = (use_vec ? A.rows : A.nblk) - n_int;
+    const bool split   = A.halo != nullptr && c.opt.overlap && c.side != nullptr && n_int > 0 && n_bnd > 0 &&
+                       A.int_row1 - A.int_row0 >= c.opt.overlap_min_rows;
+    if (!split) {
+        if (A.halo) halo_exchange(*A.halo, const_cast<double*>(a.x), a.done, a.conditional);
+        ProfScope prof(a.conditional ? a.mode + 50 : a.mode, A.rows, A.nnz, pbytes);
+        launch_any(A, v, a, 0);
+        reduce_finish(a.red, a.done);
+        return;
+    }
+    ProfScope  prof(a.conditional ? a.mode + 50 : a.mode, A.rows, A.nnz, pbytes);
+    const bool has_red = a.red.dot_out != nullptr || a.red.nrm2_out != nullptr;
+    FC_CUDA(cudaEventRecord(c.ev_fork, c.stream));
+    FC_CUDA(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+    {
+        CsrArgs ai = a;
+        if (a.red.dot_out) ai.red.dot_out = c.side_tot;
+        if (a.red.nrm2_out) ai.red.nrm2_out = c.side_tot + 1;
+        c.launch_stream = c.side;
+        try {
+            launch_any(A, v, ai, 1);
+        } catch (...) {
+            c.launch_stream = c.stream;
+            throw;
+        }
+        c.launch_stream = c.stream;
+    }
+    FC_CUDA(cudaEventRecord(c.ev_join, c.side));
+    halo_exchange(*A.halo, const_cast<double*>(a.x), a.done, a.conditional);
+    CsrArgs ab = a;
+    if (has_red) {   // the boundary kernel adds the interior's totals: it must run after the interior
+        ab.red_add = c.side_tot;
+        FC_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
+        launch_any(A, v, ab, 2);
+    } else {
+        launch_any(A, v, ab, 2);
+        FC_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
     }
     reduce_finish(a.red, a.done);
 }
@@ -707,7 +773,7 @@ static void build_rowblocks(int rows, const int* ia, int cap, int maxrows, std::
 }
 
 void csr_upload(DevCSR& d, int rows, int cols, long long nnz, const int* ia, const int* ja,
-                const double* val, bool pattern_only)
+                const double* val, bool pattern_only, int ghost_col0)
 {
     ensure_init();
     Ctx& c = ctx();
@@ -808,6 +874,36 @@ void csr_upload(DevCSR& d, int rows, int cols, long long nnz, const int* ia, con
     d.bytes += sizeof(int2) * bd.size();
     FC_CUDA(cudaStreamSynchronize(c.stream));   // host staging vectors go out of scope
     red_partials((size_t)d.nblk);
+    // multi-GPU slab: the longest run of rows that reference no ghost column (for a z-slab of a grid: everything
+    // but the planes next to the neighbours), and the row blocks that lie entirely inside it
+    d.int_row0 = d.int_row1 = d.int_blk0 = d.int_blk1 = 0;
+    if (ghost_col0 >= 0 && rows > 0) {
+        int best0 = 0, best1 = 0, run0 = 0;
+        for (int i = 0; i <= rows; ++i) {
+            bool ghost = (i == rows);
+            if (!ghost)
+                for (int k = ia[i]; k < ia[i + 1]; ++k)
+                    if (ja[k] >= ghost_col0) {
+                        ghost = true;
+                        break;
+                    }
+            if (ghost) {
+                if (i - run0 > best1 - best0) best0 = run0, best1 = i;
+                run0 = i + 1;
+            }
+        }
+        d.int_row0 = best0, d.int_row1 = best1;
+        int b0 = 0;
+        while (b0 < d.nblk && rb[b0] < best0) ++b0;
+        int b1 = b0;
+        while (b1 < d.nblk && rb[b1 + 1] <= best1) ++b1;
+        d.int_blk0 = b0, d.int_blk1 = b1;
+        // reduction scratch of the side stream, reserved before any graph capture
+        c.launch_stream = c.side;
+        const size_t vgrid = (size_t)rows * (size_t)(d.vec_lpr > 0 ? d.vec_lpr : 1) / TPB + 2;
+        red_partials(std::max((size_t)d.nblk, vgrid));
+        c.launch_stream = c.stream;
+    }
 }
 
 void csr_free(DevCSR& d)

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--vec-min-avg", type=int, default=-1)
     ap.add_argument("--opt", action="append", default=[], help="library option key=value")
     ap.add_argument("--lprs", default="", help="comma list of vec_lpr overrides to compare per level (0 = default choice)")
+    ap.add_argument("--optsets", default="", help="option sets to compare per matrix: 'k=v,k=v;k=v' (applied before the upload)")
+    ap.add_argument("--reset", default="", help="options restored after every set: 'k=v,k=v'")
     a = ap.parse_args()
     L = api.lib(); api.check(L.fasp_cuda_init(0))
     for kv in a.opt:
@@ -40,7 +42,12 @@ def main():
         for op in a.ops.split(","):
             if op != "A" and l >= nl - 1: continue
             m = getattr(mgl[l], op)
-            for lpr in ([int(v) for v in a.lprs.split(",")] if a.lprs else [None]):
+            sets = [c for c in a.optsets.split(";") if c] or [""]
+            for oset in sets:
+              for kv in [x for x in a.reset.split(",") if x] + [x for x in oset.split(",") if x]:
+                  k, v = kv.split("=")
+                  api.check(L.fasp_cuda_set_option(k.encode(), float(v)))
+              for lpr in ([int(v) for v in a.lprs.split(",")] if a.lprs else [None]):
                 if lpr is not None: L.fasp_cuda_set_option(b"vec_lpr", float(lpr))
                 h = L.fasp_cuda_dcsr_upload(C.byref(m))
                 if not h: raise RuntimeError(api.last_error())
@@ -52,7 +59,7 @@ def main():
                     if what in (10, 11): by += 24.0 * m.row
                     print(json.dumps({"level": l, "op": op, "rows": m.row, "cols": m.col, "nnz": m.nnz,
                                       "nnz_per_row": round(m.nnz / max(1, m.row), 1), "kernel": names[what], "lpr": lpr,
-                                      "us": round(ms * 1e3, 2), "GBps": round(by / ms * 1e-6, 1)}), flush=True)
+                                      "opts": oset, "us": round(ms * 1e3, 2), "GBps": round(by / ms * 1e-6, 1)}), flush=True)
                 L.fasp_cuda_dcsr_free(h)
     hf.amg_free(mgl, amg)
 

@@ -90,7 +90,7 @@ def test_bsr_mgcycle_tight_coarse_tolerance(gpu, ref, cycle, scaling):
     """The loose 1e-5 bar above is the REFERENCE's inexactness: its coarsest solve is GMRES(25) to param->tol
     (PreMGCycle.c:443-459). With that tolerance forced tight the reference cycle agrees with the device cycle
     (dense direct coarse solve) to 1e-8, for V and W cycles and with coarse-grid scaling (PreMGCycle.c:465-480)."""
-    A, b = PB.blockoil7(10)
+    A, b = PB.blockoil7(16)
     amg = _bsr_amg(ref, cycle_type=cycle, coarse_scaling=scaling, tol=1e-13)
     mgl = ref.bamg_setup(A, amg)
     try:
