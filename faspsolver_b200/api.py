@@ -65,6 +65,8 @@ def lib():
         "fasp_cuda_blas_darray_norminf": (REAL, [INT, PREAL]),
         "fasp_cuda_solver_matfree_init": (INT, [INT, P(T.mxv_matfree), vp]),
         "fasp_cuda_dense_inverse": (INT, [INT, PREAL, PREAL]),
+        "fasp_cuda_dcsr_trans": (INT, [P(dCSRmat), P(dCSRmat)]),
+        "fasp_cuda_blas_dcsr_rap": (INT, [P(dCSRmat), P(dCSRmat), P(dCSRmat), P(dCSRmat)]),
         "fasp_cuda_blas_mxv_csr": (None, [vp, PREAL, PREAL]),
         "fasp_cuda_blas_mxv_bsr": (None, [vp, PREAL, PREAL]),
         "fasp_cuda_smoother_dcsr_jacobi": (INT, [P(dvector), INT, INT, INT, P(dCSRmat), P(dvector), INT, REAL]),

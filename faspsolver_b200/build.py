@@ -38,7 +38,8 @@ def _sources():
 
 def _stamp() -> str:
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list((ROOT / "include").glob("*.h"))):
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list((ROOT / "include").glob("*.h"))
+                    + list((PKG / "cshim").glob("*.c"))):
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -78,6 +79,10 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
         print("\n".join(outs))
     _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB),
           *map(str, objs), "-ldl"])
+    # the interposition shim (plain C): FASP's own fasp_dcsr_trans / fasp_blas_dcsr_rap, forwarded to the device
+    _run(["gcc", "-O2", "-std=c99", "-Wall", "-fPIC", "-shared", f"-I{ROOT / 'include'}",
+          str(PKG / "cshim" / "interpose.c"), "-o", str(LIBDIR / "libfasp_cuda_setup.so"),
+          f"-L{LIBDIR}", "-lfasp_cuda", "-Wl,-rpath,$ORIGIN"])
     stamp_file.write_text(stamp)
     return LIB
 

@@ -481,6 +481,30 @@ INT fasp_cuda_smoother_dcsr_poly(dCSRmat* Amat, dvector* brhs, dvector* usol, IN
 }
 
 // ------------------------------------------------------------------------------------
+// setup-phase pieces on the device (setup.cu)
+// ------------------------------------------------------------------------------------
+INT fasp_cuda_dcsr_trans(const dCSRmat* A, dCSRmat* AT)
+{
+    API_TRY
+    check_csr(A);
+    if (!AT) fail(ERROR_INPUT_PAR, "fasp_cuda_dcsr_trans: null output");
+    setup_transpose(A, AT);
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+INT fasp_cuda_blas_dcsr_rap(const dCSRmat* R, const dCSRmat* A, const dCSRmat* P, dCSRmat* RAP)
+{
+    API_TRY
+    check_csr(R);
+    check_csr(A);
+    check_csr(P);
+    if (!RAP) fail(ERROR_INPUT_PAR, "fasp_cuda_blas_dcsr_rap: null output");
+    setup_rap(R, A, P, RAP);
+    return FASP_SUCCESS;
+    API_CATCH(code__)
+}
+
+// ------------------------------------------------------------------------------------
 // resident objects
 // ------------------------------------------------------------------------------------
 fasp_cuda_csr* fasp_cuda_dcsr_upload(const dCSRmat* A)

@@ -273,6 +273,12 @@ double*       red_partials(size_t nblocks);
 unsigned int* red_ticket();
 
 // ------------------------------------------------------------------------------------
+// setup-phase pieces on the device (setup.cu): A^T and R A P in the reference's output layout
+// ------------------------------------------------------------------------------------
+void setup_transpose(const dCSRmat* A, dCSRmat* AT);
+void setup_rap(const dCSRmat* R, const dCSRmat* A, const dCSRmat* P, dCSRmat* RAP);
+
+// ------------------------------------------------------------------------------------
 // timing helpers
 // ------------------------------------------------------------------------------------
 void flush_l2();

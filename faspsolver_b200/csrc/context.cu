@@ -50,8 +50,12 @@ void ensure_init()
     FC_CUDA(cudaGetDeviceProperties(&p, dev));
     c.sm_count = p.multiProcessorCount;
     c.l2_bytes = (size_t)p.l2CacheSize;
-    FC_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    FC_CUDA(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+    // the main stream carries the ghost pushes and flag barriers of the multi-GPU solve: highest priority, so
+    // that their few CTAs are placed ahead of the pending CTAs of the interior kernels on the side stream
+    int prio_lo = 0, prio_hi = 0;
+    FC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    FC_CUDA(cudaStreamCreateWithPriority(&c.stream, cudaStreamNonBlocking, prio_hi));
+    FC_CUDA(cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, prio_lo));
     c.launch_stream = c.stream;
     FC_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
     FC_CUDA(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));

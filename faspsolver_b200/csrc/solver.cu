@@ -176,9 +176,11 @@ int solver_solve_host(fasp_cuda_solver_s* s, const double* b, double* x, ITS_par
     // solver lives (a stale registration would DMA into pages the process no longer sees).
     const size_t bytes = sizeof(double) * n;
     auto pinned = [&](const void* p) -> bool {
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, p) == cudaSuccess) {
-            if (at.type == cudaMemoryTypeHost) return true;
+        // page-locked from the first to the last byte? (an application may have pinned only a slice of the array)
+        cudaPointerAttributes at, at2;
+        if (cudaPointerGetAttributes(&at, p) == cudaSuccess &&
+            cudaPointerGetAttributes(&at2, static_cast<const char*>(p) + bytes - 1) == cudaSuccess) {
+            if (at.type == cudaMemoryTypeHost && at2.type == cudaMemoryTypeHost) return true;
         } else {
             cudaGetLastError();
         }

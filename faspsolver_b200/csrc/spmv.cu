@@ -545,6 +545,10 @@ static void launch_pipe(const DevCSR& A, const CsrView& v, const CsrArgs& a, con
     if (per_sm < 1) per_sm = 1;
     if (per_sm > c.opt.pipe_ctas) per_sm = c.opt.pipe_ctas;
     if (per_sm > 2048 / T) per_sm = 2048 / T;
+    // Interior rows of a multi-GPU slab (side stream): the CTAs are persistent, so a full grid would hold every SM
+    // until the kernel ends and the ghost push / flag barrier on the main stream could not start beside it. Leave
+    // one CTA slot per SM free for them.
+    if (c.launch_stream == c.side && c.side != nullptr && per_sm > 2) per_sm -= 1;
     long long grid = (long long)c.sm_count * per_sm;
     if (grid > ur.count) grid = ur.count;
     FC_LAUNCH((csr_pipe_kernel<MODE, PATTERN, T, UG>), (int)grid, T, smem, v, a, ur, nst,

@@ -204,7 +204,7 @@ def bench_main(args):
     t_upload = time.time() - t
     r0, r1 = solver.row0, solver.row1
     nloc = r1 - r0
-    b_loc = np.ascontiguousarray(b[r0:r1])
+    b_loc = b[r0:r1].copy()   # this rank's own array (page-locked below), not a view of the global vector
     zero = np.zeros(nloc)
     log("[bench] rank 0 owns rows [%d, %d) of %d; upload %.2fs" % (r0, r1, n, t_upload))
 
@@ -280,7 +280,7 @@ def bench_main(args):
         parity = {"iters_1": int(it1), "iters_N": int(iters), "dx_rel": dx, "bar": "|iters_N - iters_1| <= 1, dx_rel <= 1e-8"}
         log("[bench] parity vs the one-GPU solve: %s" % parity)
         if it1 < 0 or abs(int(iters) - int(it1)) > 1 or not dx <= 1e-8:
-            raise RuntimeError("multi-GPU solve differs from the one-GPU solve: %s" % parity)
+            raise RuntimeError("multi-GPU solve differs from the one-GPU solve: %s (%s)" % (parity, api.last_error()))
         ms = float(np.mean(dev_ms))
         out = {
             "metric": B.METRIC, "value": ms, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,

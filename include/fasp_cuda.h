@@ -152,6 +152,21 @@ INT fasp_cuda_multicolor_host(INT n, const INT* IA, const INT* JA, INT* IC, INT*
 INT fasp_cuda_smoother_dbsr_jacobi1(dBSRmat* A, dvector* b, dvector* u, REAL* diaginv);
 
 /* ------------------------------------------------------------------------------------ */
+/* Setup-phase pieces on the device (the two matrix-matrix steps of every AMG level)      */
+/* ------------------------------------------------------------------------------------ */
+
+/* AT = A^T, host pointers; AT->IA/JA/val are calloc'ed (free them as FASP does, fasp_dcsr_free). The result is
+ * identical to the reference's, entry for entry.        replaces fasp_dcsr_trans     BlaSparseCSR.c:952 */
+INT fasp_cuda_dcsr_trans(const dCSRmat* A, dCSRmat* AT);
+/* RAP = R*A*P (Galerkin coarse operator), host pointers, output calloc'ed. Same entry ORDER inside every row
+ * (diagonal first, then first-met order of the R->A->P walk) and the same bits in every value as the
+ * reference's sequential code.                          replaces fasp_blas_dcsr_rap  BlaSpmvCSR.c:999   */
+INT fasp_cuda_blas_dcsr_rap(const dCSRmat* R, const dCSRmat* A, const dCSRmat* P, dCSRmat* RAP);
+/* libfasp_cuda_setup.so (same directory) defines fasp_dcsr_trans / fasp_blas_dcsr_rap themselves and forwards
+ * them to the two functions above: LD_PRELOAD it (or link it before libfasp) and FASP's own fasp_amg_setup_rs /
+ * _sa run their transposes and triple products on the device, unmodified. See INTEGRATION.md.             */
+
+/* ------------------------------------------------------------------------------------ */
 /* Device-resident objects                                                                */
 /* ------------------------------------------------------------------------------------ */
 

@@ -17,15 +17,17 @@ from bench_configs import blockoil7_lean
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=160)
+    ap.add_argument("--quick", action="store_true", help="only the shapes worth comparing at large sizes")
     a = ap.parse_args()
     L = api.lib(); api.check(L.fasp_cuda_init(0))
     peak, _ = B.peaks()
     A, _b = blockoil7_lean(a.n)
     by = (8.0 * 9 + 4) * A.NNZ + 4.0 * (A.ROW + 1) + 8.0 * 3 * (A.COL + A.ROW)
     print("# 3x3-block 7-point %d^3: %d block rows, %d blocks, %.2f GB per pass; peak %.0f GB/s" % (a.n, A.ROW, A.NNZ, by / 1e9, peak))
-    for rb in (32, 64):
-        for u in (4, 8):
-            for st in (2, 3):
+    combos = [(32, 4, 2), (64, 4, 2), (64, 8, 2)] if a.quick else [(rb, u, st) for rb in (32, 64) for u in (4, 8) for st in (2, 3)]
+    if True:
+        if True:
+            for rb, u, st in combos:
                 for k, v in (("bsr_rb", rb), ("bsr_u", u), ("bsr_stages", st)):
                     L.fasp_cuda_set_option(k.encode(), float(v))
                 h = L.fasp_cuda_dbsr_upload(A.ptr())

@@ -6,3 +6,10 @@ tot = 0
 for l in d['levels'][:int(sys.argv[2]) if len(sys.argv) > 2 else 16]:
     print("%9d %10d %3d %8.3f ms %7.0f GB/s  nnz/row %.1f" % (l['rows'], l['nnz'], l['launches'], l['ms'], l['GBps'], l['nnz'] / l['rows']))
 print('sum matrix-kernel ms per solve', sum(l['ms'] for l in d['levels']))
+for k, v in d.get('extra', {}).items():
+    if 'unavailable' in v:
+        print(k, v); continue
+    print(k, {a: v[a] for a in ('value', 'iterations', 'true_relres', 'levels', 'host_setup_s', 'upload_s', 'gpu_launches_per_solve', 'operator_complexity') if a in v},
+          'e2e', v['e2e']['value'], 'roofline', v['roofline'] and (round(v['roofline']['achieved']), round(v['roofline']['frac'], 3)), v.get('bsr_spmv'))
+    for l in v.get('levels_table', [])[:8]:
+        print('    ', l)

@@ -177,3 +177,25 @@ def test_c_application_links_and_fails_loudly_without_device(c_example_exe):
     r = subprocess.run([str(c_example_exe), "8", "0"], capture_output=True, text=True, env=env)
     assert r.returncode == 2, (r.returncode, r.stdout, r.stderr)
     assert "no CPU fallback" in r.stderr
+
+
+def test_setup_shim_interposes_and_fails_loudly_without_device(tmp_path):
+    """libfasp_cuda_setup.so in front of libfasp: the UNMODIFIED fasp_amg_setup_rs reaches fasp_cuda_dcsr_trans
+    through FASP's own symbol name; on a machine without a GPU that is a loud FASP-style error, not a CPU fallback."""
+    ref_lib = ROOT / "oracle" / "_ref" / "libfasp_seq.so"
+    shim = ROOT / "faspsolver_b200" / "lib" / "libfasp_cuda_setup.so"
+    if not ref_lib.exists():
+        pytest.skip("oracle/_ref/libfasp_seq.so not built")
+    assert shim.exists()
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from oracle.ref import RefFasp\n"
+        "from faspsolver_b200 import problems as PB, fasp_types as T\n"
+        "ref = RefFasp(); A = PB.poisson7(8)\n"
+        "mgl = ref.amg_setup(A, ref.amg_param(print_level=0, coarse_dof=20))\n"
+        "print('levels', mgl[0].num_levels)\n" % str(ROOT))
+    env = dict(os.environ, LD_PRELOAD=str(shim), CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "fasp_dcsr_trans on the device failed" in r.stderr and "no CPU fallback" in r.stderr
+    assert "levels" not in r.stdout
