@@ -178,6 +178,7 @@ void amg_free(Amg* h)
     for (Level& L : h->lv) {
         if (L.p2p_registered) {
             p2p_unregister(L.b), p2p_unregister(L.xa), p2p_unregister(L.xb), p2p_unregister(L.w);
+            if (L.dscale_ext) p2p_unregister(L.dscale_ext);
             for (int i = 0; i < 3; ++i)
                 if (L.pv[i]) p2p_unregister(L.pv[i]);
         }
@@ -189,6 +190,7 @@ void amg_free(Amg* h)
         dfree(L.xb);
         dfree(L.w);
         for (int i = 0; i < 3; ++i) dfree(L.pv[i]);
+        dfree(L.dscale_ext);
         dfree(L.color_rows);
         halo_free(L.hA);
         halo_free(L.hP);
@@ -215,7 +217,13 @@ struct CycleState {
     int           gs_order = 1;   // +1 pre-smoothing, -1 post-smoothing
     std::vector<double*> cur;     // current iterate buffer per level
     std::vector<bool>    xzero;   // iterate known to be identically zero
-    CycleState(Amg& h_, const int* d) : h(h_), done(d), cur(h_.nl), xzero(h_.nl, false) {}
+    // multi-GPU, redundant ghost rows: the ghost entries (in A_l's ghost layout) of the level's right-hand side /
+    // of the current iterate buffer are up to date, so the next gather of that vector needs no exchange
+    std::vector<bool>    bfresh, xfresh;
+    CycleState(Amg& h_, const int* d)
+        : h(h_), done(d), cur(h_.nl), xzero(h_.nl, false), bfresh(h_.nl, false), xfresh(h_.nl, false)
+    {
+    }
     const double* rhs(int l) const { return l == 0 ? b0 : h.lv[l].b; }
     double*       other(int l) const
     {
@@ -241,20 +249,30 @@ void smooth(CycleState& s, int l, int nsweeps, bool last)
                 double*    out = final_sweep ? s.x_out : s.other(l);
                 Reduce     red = final_sweep ? s.red : Reduce();
                 if (s.xzero[l] && ctx().opt.zero_guess) {
-                    vec_scale_div(out, jac ? h.relax : 1.0, b, jac ? L.A.diag : L.A.l1, n, red,
-                                  s.done);
+                    // with the ghost rows of b at hand (R computed them) the sweep covers them as well: the
+                    // residual that follows then needs no exchange of x
+                    const bool ext = s.bfresh[l] && L.dscale_ext != nullptr && !red.dot_out && !red.nrm2_out;
+                    vec_scale_div(out, jac ? h.relax : 1.0, b, ext ? L.dscale_ext : (jac ? L.A.diag : L.A.l1),
+                                  ext ? n + (size_t)L.A.nghost : n, red, s.done);
+                    s.xfresh[l] = ext;
                 } else {
-                    if (s.xzero[l]) vec_set(s.cur[l], 0.0, n, s.done);
+                    if (s.xzero[l]) {
+                        vec_set(s.cur[l], 0.0, n, s.done);
+                        s.xfresh[l] = false;
+                    }
                     CsrArgs a;
-                    a.mode  = jac ? CSR_JACOBI : CSR_L1;
-                    a.alpha = h.relax;
-                    a.x     = s.cur[l];
-                    a.b     = b;
-                    a.y     = out;
-                    a.red   = red;
-                    a.done  = s.done;
+                    a.mode      = jac ? CSR_JACOBI : CSR_L1;
+                    a.alpha     = h.relax;
+                    a.x         = s.cur[l];
+                    a.b         = b;
+                    a.y         = out;
+                    a.red       = red;
+                    a.done      = s.done;
+                    a.skip_halo = s.xfresh[l];
                     csr_launch(L.A, a);
+                    s.xfresh[l] = false;   // the sweep writes another buffer: owned rows only
                 }
+                s.bfresh[l] = false;
                 if (final_sweep) s.red_done = true;
                 s.cur[l]   = out;
                 s.xzero[l] = false;
@@ -266,6 +284,7 @@ void smooth(CycleState& s, int l, int nsweeps, bool last)
                 if (s.xzero[l]) vec_set(s.cur[l], 0.0, n, s.done);
                 gs_multicolor_sweeps(L.A, L.color_rows, L.color_ptr, b, s.cur[l], 1, s.gs_order, s.done);
                 s.xzero[l] = false;
+                s.xfresh[l] = s.bfresh[l] = false;
                 break;
             }
             case SMOOTHER_POLY: {
@@ -280,16 +299,19 @@ void smooth(CycleState& s, int l, int nsweeps, bool last)
                         vec_mul(rbar, L.A.dinv, b, n, s.done);
                     }
                 }
+                if (s.xzero[l]) s.xfresh[l] = false;
                 if (r == L.w) {
                     CsrArgs a;
-                    a.mode   = CSR_RESID_DINV;
-                    a.x      = u;
-                    a.b      = b;
-                    a.y      = L.w;
-                    a.v0_out = rbar;
-                    a.done   = s.done;
+                    a.mode      = CSR_RESID_DINV;
+                    a.x         = u;
+                    a.b         = b;
+                    a.y         = L.w;
+                    a.v0_out    = rbar;
+                    a.done      = s.done;
+                    a.skip_halo = s.xfresh[l];
                     csr_launch(L.A, a);
                 }
+                s.xfresh[l] = s.bfresh[l] = false;   // u += error below touches owned rows only
                 double* v0 = L.pv[1];
                 double* v1 = L.pv[2];
                 {
@@ -371,12 +393,14 @@ void run_cycle(CycleState& s)
                 s.xzero[l] = false;
             }
             CsrArgs a;   // w = b - A x   (copy + aAxpy(-1), PreMGCycle.c:136-137)
-            a.mode = CSR_RESID;
-            a.x    = s.cur[l];
-            a.b    = s.rhs(l);
-            a.y    = L.w;
-            a.done = s.done;
+            a.mode      = CSR_RESID;
+            a.x         = s.cur[l];
+            a.b         = s.rhs(l);
+            a.y         = L.w;
+            a.done      = s.done;
+            a.skip_halo = s.xfresh[l];
             csr_launch(L.A, a);
+            if (L.dist) s.xfresh[l] = true;   // exchanged or computed: the ghosts of this buffer are current
             CsrArgs r;   // b_{l+1} = R w  (:140-147; pattern-only for UA)
             r.mode = CSR_MXV;
             r.x    = L.w;
@@ -388,8 +412,10 @@ void run_cycle(CycleState& s)
             if (gather_next)
                 comm_allgatherv(r.y, L.gcounts[comm_rank()], h.lv[l + 1].b, L.gcounts, L.gdispls, s.done);
             ++l;
-            s.cur[l]   = h.lv[l].xa;
-            s.xzero[l] = true;   // fasp_dvec_set(..., 0.0) (:151) is folded into the next writer
+            s.cur[l]    = h.lv[l].xa;
+            s.xzero[l]  = true;   // fasp_dvec_set(..., 0.0) (:151) is folded into the next writer
+            s.xfresh[l] = false;
+            s.bfresh[l] = h.lv[l - 1].r_ext;   // R also produced the ghost rows of this level's right-hand side
         }
 
         coarse_solve(s, false);
@@ -420,6 +446,8 @@ void run_cycle(CycleState& s)
                 p.alpha_dev = h.scal;
             }
             csr_launch(L.P, p);
+            // P with ghost rows appended also updated the ghost entries of x_l (they were current before)
+            s.xfresh[l] = L.p_ext && s.xfresh[l];
             // the cycle ends when the backward sweep reaches level 0
             const bool last_level_visit = (l == 0);
             s.gs_order = -1;

@@ -40,6 +40,10 @@ struct Level {
     std::vector<size_t> gcounts, gdispls;   // next level replicated: every rank's slice of its vectors
     HaloPlan *hA = nullptr, *hP = nullptr, *hR = nullptr;
     bool    p2p_registered = false;
+    // redundant ghost rows (dist.cu): P_l also updates the ghost entries of x_l (those A_l gathers), R_l also
+    // produces the ghost entries of b_{l+1}; dscale_ext = the smoother's divisor (l1 / diagonal) incl. ghost rows
+    bool    p_ext = false, r_ext = false;
+    double* dscale_ext = nullptr;
     double* b  = nullptr;     // right-hand side on this level (level 0: caller's r)
     double* xa = nullptr;     // iterate ping-pong buffers
     double* xb = nullptr;

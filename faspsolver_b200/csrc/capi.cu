@@ -169,6 +169,7 @@ static int* option_slot(const char* key)
     if (!strcmp(key, "wide_threads")) return &o.wide_threads;
     if (!strcmp(key, "vec_lpr")) return &o.vec_lpr;
     if (!strcmp(key, "gs_multicolor")) return &o.gs_multicolor;
+    if (!strcmp(key, "ghost_redundant")) return &o.ghost_redundant;
     if (!strcmp(key, "overlap")) return &o.overlap;
     if (!strcmp(key, "overlap_min_rows")) return &o.overlap_min_rows;
     if (!strcmp(key, "bsr_rb")) return &o.bsr_rb;

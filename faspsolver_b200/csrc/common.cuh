@@ -69,6 +69,8 @@ struct Options {
     int    vec_lpr          = 0;   // > 0: force this many lanes per row in the vector kernel
     int    gs_multicolor    = 0;   // accept SMOOTHER_GS in the cycle as multicolour GS (OpenMP-FASP semantics)
     int    profile          = 0;   // record CUDA events around every matrix kernel (no graphs)
+    int    ghost_redundant  = 1;   // multi-GPU: P and R also compute the ghost rows of the level they write to, so the
+                                   // post-smoother and the residual start without their own ghost exchange (2 per level)
     int    overlap          = 1;   // multi-GPU: rows without ghost columns run on a second stream while the ghosts travel
     int    overlap_min_rows = 256; // ... when the operator's interior has at least this many rows
     int    bsr_rb           = 64;  // BSR pipelined kernel: block rows per CTA (32 / 64), nb <= 4. Measured on the 3x3-block
@@ -238,6 +240,7 @@ struct CsrArgs {
     double        k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0;
     Reduce        red;
     const double* red_add = nullptr;     // totals of the other part of a split launch, added in the finalize step
+    bool          skip_halo = false;     // multi-GPU: the ghosts of x are already up to date (computed redundantly)
     const int*    done = nullptr;
     bool          conditional = false;   // launch gated by a rarely-taken branch flag (profiling tag)
 };

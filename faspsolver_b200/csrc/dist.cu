@@ -80,41 +80,63 @@ static int owner_of(const std::vector<int>& off, int c)
 }
 
 void dist_extract(const dCSRmat& A, int r0, int r1, const std::vector<int>& coff, int rank, bool pattern_only,
-                  LocalCSR& out)
+                  LocalCSR& out, const std::vector<int>& extra)
 {
-    out.rows = r1 - r0;
+    const int nown = r1 - r0;
+    out.rows       = nown + (int)extra.size();
     out.ia.resize((size_t)out.rows + 1);
-    const int k0 = A.IA[r0], k1 = A.IA[r1];
-    out.ja.resize((size_t)(k1 - k0));
+    auto grow = [&](int i) { return i < nown ? r0 + i : extra[(size_t)(i - nown)]; };   // local row -> global row
+    long long nnz = 0;
+    for (int i = 0; i < out.rows; ++i) {
+        out.ia[i] = (int)nnz;
+        const int g = grow(i);
+        nnz += A.IA[g + 1] - A.IA[g];
+    }
+    out.ia[out.rows] = (int)nnz;
+    out.ja.resize((size_t)nnz);
     out.val.clear();
-    if (!pattern_only && A.val) out.val.assign(A.val + k0, A.val + k1);
-    for (int i = r0; i <= r1; ++i) out.ia[i - r0] = A.IA[i] - k0;
+    const bool vals = !pattern_only && A.val;
+    if (vals) out.val.resize((size_t)nnz);
+    for (int i = 0; i < out.rows; ++i) {
+        const int g = grow(i), k0 = A.IA[g], len = A.IA[g + 1] - k0;
+        std::copy(A.JA + k0, A.JA + k0 + len, out.ja.begin() + out.ia[i]);   // global columns for now
+        if (vals) std::copy(A.val + k0, A.val + k0 + len, out.val.begin() + out.ia[i]);
+    }
     out.ghosts.clear();
     if (coff.empty()) {   // replicated column space: global numbering
-        for (int k = k0; k < k1; ++k) out.ja[k - k0] = A.JA[k];
         out.cols = A.col;
         return;
     }
     const int c0 = coff[rank], c1 = coff[rank + 1];
-    for (int k = k0; k < k1; ++k) {
-        const int c = A.JA[k];
+    for (int c : out.ja)
         if (c < c0 || c >= c1) out.ghosts.push_back(c);
-    }
     std::sort(out.ghosts.begin(), out.ghosts.end());
     out.ghosts.erase(std::unique(out.ghosts.begin(), out.ghosts.end()), out.ghosts.end());
     const int nloc = c1 - c0;
-    for (int k = k0; k < k1; ++k) {
-        const int c = A.JA[k];
-        if (c >= c0 && c < c1) out.ja[k - k0] = c - c0;
-        else
-            out.ja[k - k0] =
-                nloc + (int)(std::lower_bound(out.ghosts.begin(), out.ghosts.end(), c) - out.ghosts.begin());
+    for (int& c : out.ja) {
+        if (c >= c0 && c < c1) c -= c0;
+        else c = nloc + (int)(std::lower_bound(out.ghosts.begin(), out.ghosts.end(), c) - out.ghosts.begin());
     }
     out.cols = nloc + (int)out.ghosts.size();
 }
 
+void dist_ghost_lists(const dCSRmat& A, const std::vector<int>& off, std::vector<std::vector<int>>& ghosts)
+{
+    const int nr = (int)off.size() - 1;
+    ghosts.assign(nr, std::vector<int>());
+    for (int q = 0; q < nr; ++q) {
+        std::vector<int>& g = ghosts[q];
+        for (int k = A.IA[off[q]]; k < A.IA[off[q + 1]]; ++k) {
+            const int c = A.JA[k];
+            if (c < off[q] || c >= off[q + 1]) g.push_back(c);
+        }
+        std::sort(g.begin(), g.end());
+        g.erase(std::unique(g.begin(), g.end()), g.end());
+    }
+}
+
 void dist_send_lists(const dCSRmat& A, const std::vector<int>& roff, const std::vector<int>& coff, int rank,
-                     std::vector<std::vector<int>>& send)
+                     std::vector<std::vector<int>>& send, const std::vector<std::vector<int>>* extra_by_rank)
 {
     const int nr = (int)roff.size() - 1;
     send.assign(nr, std::vector<int>());
@@ -124,10 +146,15 @@ void dist_send_lists(const dCSRmat& A, const std::vector<int>& roff, const std::
         if (q == rank) continue;
         std::fill(mark.begin(), mark.end(), 0);
         bool any = false;
-        for (int k = A.IA[roff[q]]; k < A.IA[roff[q + 1]]; ++k) {
-            const int c = A.JA[k];
-            if (c >= c0 && c < c1) mark[c - c0] = 1, any = true;
-        }
+        auto scan = [&](int k0, int k1) {
+            for (int k = k0; k < k1; ++k) {
+                const int c = A.JA[k];
+                if (c >= c0 && c < c1) mark[c - c0] = 1, any = true;
+            }
+        };
+        scan(A.IA[roff[q]], A.IA[roff[q + 1]]);
+        if (extra_by_rank)
+            for (int g : (*extra_by_rank)[q]) scan(A.IA[g], A.IA[g + 1]);
         if (!any) continue;
         for (int c = 0; c < c1 - c0; ++c)
             if (mark[c]) send[q].push_back(c);   // ascending local index = ascending global index
@@ -136,7 +163,7 @@ void dist_send_lists(const dCSRmat& A, const std::vector<int>& roff, const std::
 
 // plan + upload of one partitioned operator
 static HaloPlan* make_plan(const dCSRmat& A, const std::vector<int>& roff, const std::vector<int>& coff,
-                           const LocalCSR& loc, int rank)
+                           const LocalCSR& loc, int rank, const std::vector<std::vector<int>>* extra_by_rank)
 {
     HaloPlan* h = new HaloPlan();
     h->nloc     = coff[rank + 1] - coff[rank];
@@ -151,7 +178,7 @@ static HaloPlan* make_plan(const dCSRmat& A, const std::vector<int>& roff, const
         h->recv_cnt.push_back((int)(g - b));
     }
     std::vector<std::vector<int>> send;
-    dist_send_lists(A, roff, coff, rank, send);
+    dist_send_lists(A, roff, coff, rank, send, extra_by_rank);
     std::vector<int> idx;
     for (int q = 0; q < (int)send.size(); ++q) {
         if (send[q].empty()) continue;
@@ -187,16 +214,20 @@ static HaloPlan* make_plan(const dCSRmat& A, const std::vector<int>& roff, const
     return h;
 }
 
+// extra_by_rank: rows every rank computes in addition to its slab (the ghost rows of the level the operator
+// writes to); the local operator gets them appended behind the owned rows.
 static HaloPlan* upload_part(DevCSR& d, const dCSRmat& A, const std::vector<int>& roff,
-                             const std::vector<int>& coff, int rank, bool pattern)
+                             const std::vector<int>& coff, int rank, bool pattern,
+                             const std::vector<std::vector<int>>* extra_by_rank = nullptr)
 {
     LocalCSR loc;
-    dist_extract(A, roff[rank], roff[rank + 1], coff, rank, pattern, loc);
+    static const std::vector<int> none;
+    dist_extract(A, roff[rank], roff[rank + 1], coff, rank, pattern, loc, extra_by_rank ? (*extra_by_rank)[rank] : none);
     const int nloc_cols = coff.empty() ? -1 : coff[rank + 1] - coff[rank];   // columns behind it are ghosts
     csr_upload(d, loc.rows, loc.cols, (long long)loc.ja.size(), loc.ia.data(), loc.ja.data(),
                loc.val.empty() ? nullptr : loc.val.data(), pattern, nloc_cols);
     if (coff.empty()) return nullptr;
-    HaloPlan* h = make_plan(A, roff, coff, loc, rank);
+    HaloPlan* h = make_plan(A, roff, coff, loc, rank, extra_by_rank);
     d.halo      = h;
     d.nghost    = h->nghost;
     return h;
@@ -235,6 +266,16 @@ Amg* dist_amg_upload(AMG_data* mgl, AMG_param* param, int agg_rows)
         h->off0 = off[0];
         h->lv.resize(nl);
         const bool ua = (param->AMG_type == UA_AMG);
+        // Redundant ghost rows: a ghost exchange is a synchronisation of all ranks (push + flag barrier, ~15 us), and
+        // a level of the cycle needs four of them (x before the residual, w before R, x_{l+1} before P, x before the
+        // post-smoother). Two go away when a rank ALSO computes, with the same kernels and therefore the same bits,
+        // the few rows its neighbours own but its A_l gathers: P_l gets the ghost rows of x_l appended (the
+        // post-smoother then finds its ghosts up to date), R_l the ghost rows of b_{l+1} (the zero-guess pre-smoothing
+        // sweep x = b / d and the residual then need none). The price: slightly longer exchanges for w_l and x_{l+1}.
+        const bool redundant = ctx().opt.ghost_redundant != 0;
+        std::vector<std::vector<std::vector<int>>> GA(lrep);   // [level][rank] ghost columns of A_l's slab
+        if (redundant)
+            for (int l = 0; l < lrep; ++l) dist_ghost_lists(mgl[l].A, off[l], GA[l]);
         for (int l = 0; l < nl; ++l) {
             Level&         L = h->lv[l];
             const dCSRmat& A = mgl[l].A;
@@ -245,12 +286,15 @@ Amg* dist_amg_upload(AMG_data* mgl, AMG_param* param, int agg_rows)
                 L.n    = off[l][rank + 1] - off[l][rank];
                 L.hA   = upload_part(L.A, A, off[l], off[l], rank, false);
                 int ghost = L.A.nghost;
-                // R_l: rows = my slice of level l+1, gathers the level-l residual
-                L.hR = upload_part(L.R, mgl[l].R, off[l + 1], off[l], rank, ua);
-                if (L.R.nghost > ghost) ghost = L.R.nghost;
-                // P_l: my fine rows, gathers x_{l+1} (partitioned or replicated)
                 const bool next_dist = (l + 1 < lrep);
-                L.hP = upload_part(L.P, mgl[l].P, off[l], next_dist ? off[l + 1] : none, rank, ua);
+                // R_l: rows = my slice of level l+1 (+ the ghost rows of b_{l+1}), gathers the level-l residual
+                L.r_ext = redundant && next_dist;
+                L.hR    = upload_part(L.R, mgl[l].R, off[l + 1], off[l], rank, ua, L.r_ext ? &GA[l + 1] : nullptr);
+                if (L.R.nghost > ghost) ghost = L.R.nghost;
+                // P_l: my fine rows (+ the ghost rows of x_l), gathers x_{l+1} (partitioned or replicated)
+                L.p_ext = redundant;
+                L.hP    = upload_part(L.P, mgl[l].P, off[l], next_dist ? off[l + 1] : none, rank, ua,
+                                      L.p_ext ? &GA[l] : nullptr);
                 if (l > 0 && h->lv[l - 1].P.nghost > ghost) ghost = h->lv[l - 1].P.nghost;
                 L.cap = L.n + ghost;
                 if (!next_dist) {
@@ -297,6 +341,18 @@ Amg* dist_amg_upload(AMG_data* mgl, AMG_param* param, int agg_rows)
                 for (int i = 0; i < 3; ++i)
                     if (L.pv[i]) p2p_register(L.pv[i], bytes);
                 L.p2p_registered = true;
+                // the zero-guess sweep x = b / d on the ghost rows needs d there: exchanged once, here
+                if (L.dist && redundant && (h->smoother == SMOOTHER_JACOBI || h->smoother == SMOOTHER_L1DIAG) && l < nl - 1) {
+                    const double* src = (h->smoother == SMOOTHER_JACOBI) ? L.A.diag : L.A.l1;
+                    L.dscale_ext      = dalloc<double>((size_t)L.cap + 8);
+                    FC_CUDA(cudaMemsetAsync(L.dscale_ext, 0, sizeof(double) * ((size_t)L.cap + 8), ctx().stream));
+                    FC_CUDA(cudaMemcpyAsync(L.dscale_ext, src, sizeof(double) * (size_t)L.n, cudaMemcpyDeviceToDevice,
+                                            ctx().stream));
+                    p2p_register(L.dscale_ext, bytes);
+                    halo_exchange(*L.hA, L.dscale_ext);
+                    FC_CUDA(cudaStreamSynchronize(ctx().stream));
+                    h->bytes += bytes;
+                }
             }
             h->bytes += L.A.bytes + L.P.bytes + L.R.bytes;
         }

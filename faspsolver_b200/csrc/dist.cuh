@@ -33,12 +33,18 @@ struct LocalCSR {
     std::vector<int>    ghosts;      // global column of every ghost, ascending
     int                 rows = 0, cols = 0;
 };
+// `extra`: further global rows appended behind the contiguous block [r0, r1) (the ghost rows a rank computes
+// redundantly, see dist.cu); may be empty.
 void dist_extract(const dCSRmat& A, int r0, int r1, const std::vector<int>& coff, int rank, bool pattern_only,
-                  LocalCSR& out);
+                  LocalCSR& out, const std::vector<int>& extra = std::vector<int>());
 // Send lists: which of my owned columns [coff[rank], coff[rank+1]) the rows of every other rank
-// reference (computed from the global matrix every rank holds on the host; no communication).
+// reference (computed from the global matrix every rank holds on the host; no communication). `extra_by_rank`
+// (optional): the extra rows of every rank.
 void dist_send_lists(const dCSRmat& A, const std::vector<int>& roff, const std::vector<int>& coff, int rank,
-                     std::vector<std::vector<int>>& send);
+                     std::vector<std::vector<int>>& send,
+                     const std::vector<std::vector<int>>* extra_by_rank = nullptr);
+// ghost columns (global, ascending) of every rank's row slab of a square level operator
+void dist_ghost_lists(const dCSRmat& A, const std::vector<int>& off, std::vector<std::vector<int>>& ghosts);
 
 // Upload: levels with >= agg_rows global rows are partitioned, the rest replicated.
 Amg* dist_amg_upload(AMG_data* mgl, AMG_param* param, int agg_rows);

@@ -654,10 +654,11 @@ void csr_launch(const DevCSR& A, const CsrArgs& a_in)
     const bool use_vec = A.vec_lpr > 0 && !c.opt.strict;
     const int  n_int   = use_vec ? A.int_row1 - A.int_row0 : A.int_blk1 - A.int_blk0;
     const int  n_bnd   = (use_vec ? A.rows : A.nblk) - n_int;
-    const bool split   = A.halo != nullptr && c.opt.overlap && c.side != nullptr && n_int > 0 && n_bnd > 0 &&
+    const bool exch    = A.halo != nullptr && !a.skip_halo;
+    const bool split   = exch && c.opt.overlap && c.side != nullptr && n_int > 0 && n_bnd > 0 &&
                        A.int_row1 - A.int_row0 >= c.opt.overlap_min_rows;
     if (!split) {
-        if (A.halo) halo_exchange(*A.halo, const_cast<double*>(a.x), a.done, a.conditional);
+        if (exch) halo_exchange(*A.halo, const_cast<double*>(a.x), a.done, a.conditional);
         ProfScope prof(a.conditional ? a.mode + 50 : a.mode, A.rows, A.nnz, pbytes);
         launch_any(A, v, a, 0);
         reduce_finish(a.red, a.done);

@@ -43,6 +43,21 @@ for smoother, solver_type in ((T.SMOOTHER_L1DIAG, T.SOLVER_CG), (T.SMOOTHER_JACO
     api.check(L.fasp_cuda_dvec_d2h(T.as_preal(x_dev), d_x, nloc))
     L.fasp_cuda_dvec_free(d_b); L.fasp_cuda_dvec_free(d_x)
     assert st_dev == st and np.array_equal(x_dev, x_loc), (rank, st, st_dev, np.abs(x_dev - x_loc).max())
+    # the exchange-saving variants: redundant ghost rows off (bit-identical), overlap off (same to rounding)
+    for opts in ((("ghost_redundant", 0.0),), (("overlap", 0.0),), (("ghost_redundant", 0.0), ("overlap", 0.0))):
+        for k, v in opts:
+            api.check(L.fasp_cuda_set_option(k.encode(), v))
+        s2 = MG.DistSolver(mgl, amg, agg_rows=2000)
+        st2, x2 = s2.solve(b_loc, np.zeros(nloc), it)
+        s2.close()
+        for k, v in opts:
+            api.check(L.fasp_cuda_set_option(k.encode(), 1.0))
+        if opts == (("ghost_redundant", 0.0),):
+            # redundantly computed ghost rows carry the owners' bits: nothing may change
+            assert st2 == st and np.array_equal(x2, x_loc), (rank, opts, st, st2, np.abs(x2 - x_loc).max())
+        else:
+            # without the interior / boundary split the fused dot products are summed in one piece instead of two
+            assert st2 == st and np.abs(x2 - x_loc).max() <= 1e-10 * np.abs(x_loc).max(), (rank, opts, st, st2)
     parts = [None] * world
     dist.all_gather_object(parts, (s.row0, x_loc))
     s.close()
