@@ -133,6 +133,7 @@ def lib():
         "fasp_cuda_comm_size": (C.c_int, []),
         "fasp_cuda_comm_peer_memory": (C.c_int, []),
         "fasp_cuda_dist_krylov_amg_create": (vp, [P(AMG_data), P(AMG_param), INT]),
+        "fasp_cuda_dist_krylov_amg_create_slabs": (vp, [INT, P(T.fasp_cuda_slab_level), T.PINT, P(AMG_data), P(AMG_param)]),
         "fasp_cuda_dist_row_range": (INT, [vp, T.PINT, T.PINT]),
         "fasp_cuda_dist_extract_host": (INT, [P(dCSRmat), INT, INT, T.PINT, T.PINT, T.PINT, INT, T.PINT, T.PINT, INT, T.PINT]),
     }

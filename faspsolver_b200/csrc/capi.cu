@@ -1537,6 +1537,15 @@ fasp_cuda_solver* fasp_cuda_dist_krylov_amg_create(AMG_data* mgl, AMG_param* amg
     API_CATCH(nullptr)
 }
 
+fasp_cuda_solver* fasp_cuda_dist_krylov_amg_create_slabs(INT nlev, const fasp_cuda_slab_level* levels,
+                                                         const INT* tail_row_off, AMG_data* tail,
+                                                         AMG_param* amgparam)
+{
+    API_TRY
+    return solver_create_dist_slabs(nlev, levels, tail_row_off, tail, amgparam);
+    API_CATCH(nullptr)
+}
+
 INT fasp_cuda_dist_row_range(const fasp_cuda_solver* s, INT* row_begin, INT* row_end)
 {
     if (!s || !s->amg) return ERROR_INPUT_PAR;

@@ -54,6 +54,9 @@ void ensure_init()
     // that their few CTAs are placed ahead of the pending CTAs of the interior kernels on the side stream
     int prio_lo = 0, prio_hi = 0;
     FC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (const char* e = getenv("FASP_CUDA_STREAM_PRIO")) {   // 0: both streams at the default priority (A/B measurements)
+        if (atoi(e) == 0) prio_lo = prio_hi = 0;
+    }
     FC_CUDA(cudaStreamCreateWithPriority(&c.stream, cudaStreamNonBlocking, prio_hi));
     FC_CUDA(cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, prio_lo));
     c.launch_stream = c.stream;

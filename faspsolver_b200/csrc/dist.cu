@@ -102,9 +102,15 @@ void dist_extract(const dCSRmat& A, int r0, int r1, const std::vector<int>& coff
         std::copy(A.JA + k0, A.JA + k0 + len, out.ja.begin() + out.ia[i]);   // global columns for now
         if (vals) std::copy(A.val + k0, A.val + k0 + len, out.val.begin() + out.ia[i]);
     }
+    dist_renumber(out, A.col, coff, rank);
+}
+
+// columns of a slab (global numbers in out.ja) -> [owned | ghosts ascending]; fills out.ghosts / out.cols
+void dist_renumber(LocalCSR& out, int global_cols, const std::vector<int>& coff, int rank)
+{
     out.ghosts.clear();
     if (coff.empty()) {   // replicated column space: global numbering
-        out.cols = A.col;
+        out.cols = global_cols;
         return;
     }
     const int c0 = coff[rank], c1 = coff[rank + 1];
@@ -162,8 +168,19 @@ void dist_send_lists(const dCSRmat& A, const std::vector<int>& roff, const std::
 }
 
 // plan + upload of one partitioned operator
+static HaloPlan* plan_from_send_lists(const std::vector<int>& coff, const LocalCSR& loc, int rank,
+                                      const std::vector<std::vector<int>>& send);
+
 static HaloPlan* make_plan(const dCSRmat& A, const std::vector<int>& roff, const std::vector<int>& coff,
                            const LocalCSR& loc, int rank, const std::vector<std::vector<int>>* extra_by_rank)
+{
+    std::vector<std::vector<int>> send;
+    dist_send_lists(A, roff, coff, rank, send, extra_by_rank);
+    return plan_from_send_lists(coff, loc, rank, send);
+}
+
+static HaloPlan* plan_from_send_lists(const std::vector<int>& coff, const LocalCSR& loc, int rank,
+                                      const std::vector<std::vector<int>>& send)
 {
     HaloPlan* h = new HaloPlan();
     h->nloc     = coff[rank + 1] - coff[rank];
@@ -177,8 +194,6 @@ static HaloPlan* make_plan(const dCSRmat& A, const std::vector<int>& roff, const
         h->recv_off.push_back((int)b);
         h->recv_cnt.push_back((int)(g - b));
     }
-    std::vector<std::vector<int>> send;
-    dist_send_lists(A, roff, coff, rank, send, extra_by_rank);
     std::vector<int> idx;
     for (int q = 0; q < (int)send.size(); ++q) {
         if (send[q].empty()) continue;
@@ -231,6 +246,47 @@ static HaloPlan* upload_part(DevCSR& d, const dCSRmat& A, const std::vector<int>
     d.halo      = h;
     d.nghost    = h->nghost;
     return h;
+}
+
+// vectors of one level: identical capacity on every rank, peer mapping, the smoother divisor on the ghost rows
+static void finish_level(Amg& h, Level& L, int l, int lrep, bool redundant)
+{
+    const int nl = h.nl;
+    if (comm_active() && (l <= lrep)) {
+        // identical vector capacity on every rank (peer addresses = same offsets)
+        double  c  = (double)(L.cap > L.n ? L.cap : L.n);
+        double* dc = dalloc<double>(1);
+        FC_CUDA(cudaMemcpyAsync(dc, &c, 8, cudaMemcpyHostToDevice, ctx().stream));
+        comm_allreduce(dc, 1, 2);
+        FC_CUDA(cudaMemcpyAsync(&c, dc, 8, cudaMemcpyDeviceToHost, ctx().stream));
+        FC_CUDA(cudaStreamSynchronize(ctx().stream));
+        dfree(dc);
+        L.cap = (int)c;
+        if (l == 0) L.A.vec_cap = L.cap;
+    }
+    amg_level_vectors(h, L);
+    if (l <= lrep) {   // partitioned levels + the first replicated one (all-gather target)
+        const size_t bytes = sizeof(double) * ((size_t)L.cap + 8);
+        p2p_register(L.b, bytes);
+        p2p_register(L.xa, bytes);
+        p2p_register(L.xb, bytes);
+        p2p_register(L.w, bytes);
+        for (int i = 0; i < 3; ++i)
+            if (L.pv[i]) p2p_register(L.pv[i], bytes);
+        L.p2p_registered = true;
+        // the zero-guess sweep x = b / d on the ghost rows needs d there: exchanged once, here
+        if (L.dist && redundant && (h.smoother == SMOOTHER_JACOBI || h.smoother == SMOOTHER_L1DIAG) && l < nl - 1) {
+            const double* src = (h.smoother == SMOOTHER_JACOBI) ? L.A.diag : L.A.l1;
+            L.dscale_ext      = dalloc<double>((size_t)L.cap + 8);
+            FC_CUDA(cudaMemsetAsync(L.dscale_ext, 0, sizeof(double) * ((size_t)L.cap + 8), ctx().stream));
+            FC_CUDA(cudaMemcpyAsync(L.dscale_ext, src, sizeof(double) * (size_t)L.n, cudaMemcpyDeviceToDevice,
+                                    ctx().stream));
+            p2p_register(L.dscale_ext, bytes);
+            halo_exchange(*L.hA, L.dscale_ext);
+            FC_CUDA(cudaStreamSynchronize(ctx().stream));
+            h.bytes += bytes;
+        }
+    }
 }
 
 Amg* dist_amg_upload(AMG_data* mgl, AMG_param* param, int agg_rows)
@@ -319,46 +375,169 @@ Amg* dist_amg_upload(AMG_data* mgl, AMG_param* param, int agg_rows)
                     amg_level_smoother_data(*h, L, &A);
                 }
             }
-            if (comm_active() && (l <= lrep)) {
-                // identical vector capacity on every rank (peer addresses = same offsets)
-                double  c  = (double)(L.cap > L.n ? L.cap : L.n);
-                double* dc = dalloc<double>(1);
-                FC_CUDA(cudaMemcpyAsync(dc, &c, 8, cudaMemcpyHostToDevice, ctx().stream));
-                comm_allreduce(dc, 1, 2);
-                FC_CUDA(cudaMemcpyAsync(&c, dc, 8, cudaMemcpyDeviceToHost, ctx().stream));
-                FC_CUDA(cudaStreamSynchronize(ctx().stream));
-                dfree(dc);
-                L.cap = (int)c;
-                if (l == 0) L.A.vec_cap = L.cap;
-            }
-            amg_level_vectors(*h, L);
-            if (l <= lrep) {   // partitioned levels + the first replicated one (all-gather target)
-                const size_t bytes = sizeof(double) * ((size_t)L.cap + 8);
-                p2p_register(L.b, bytes);
-                p2p_register(L.xa, bytes);
-                p2p_register(L.xb, bytes);
-                p2p_register(L.w, bytes);
-                for (int i = 0; i < 3; ++i)
-                    if (L.pv[i]) p2p_register(L.pv[i], bytes);
-                L.p2p_registered = true;
-                // the zero-guess sweep x = b / d on the ghost rows needs d there: exchanged once, here
-                if (L.dist && redundant && (h->smoother == SMOOTHER_JACOBI || h->smoother == SMOOTHER_L1DIAG) && l < nl - 1) {
-                    const double* src = (h->smoother == SMOOTHER_JACOBI) ? L.A.diag : L.A.l1;
-                    L.dscale_ext      = dalloc<double>((size_t)L.cap + 8);
-                    FC_CUDA(cudaMemsetAsync(L.dscale_ext, 0, sizeof(double) * ((size_t)L.cap + 8), ctx().stream));
-                    FC_CUDA(cudaMemcpyAsync(L.dscale_ext, src, sizeof(double) * (size_t)L.n, cudaMemcpyDeviceToDevice,
-                                            ctx().stream));
-                    p2p_register(L.dscale_ext, bytes);
-                    halo_exchange(*L.hA, L.dscale_ext);
-                    FC_CUDA(cudaStreamSynchronize(ctx().stream));
-                    h->bytes += bytes;
-                }
-            }
+            finish_level(*h, L, l, lrep, redundant);
             h->bytes += L.A.bytes + L.P.bytes + L.R.bytes;
         }
         h->scal = dalloc<double>(4);
         FC_CUDA(cudaMemsetAsync(h->scal, 0, 4 * sizeof(double), ctx().stream));
         amg_setup_coarse(*h);   // replicated coarsest level: every rank factors / iterates redundantly
+        FC_CUDA(cudaStreamSynchronize(ctx().stream));
+    } catch (...) {
+        amg_free(h);
+        throw;
+    }
+    return h;
+}
+
+// ------------------------------------------------------------------------------------
+// The same hierarchy from per-rank slabs (no global matrix on any rank; include/fasp_cuda.h
+// fasp_cuda_dist_krylov_amg_create_slabs, host side: faspsolver_b200/slabsetup.py)
+// ------------------------------------------------------------------------------------
+// every rank's list, variable length (collective)
+static void allgather_lists(const std::vector<int>& mine, std::vector<std::vector<int>>& all)
+{
+    const int        nr = comm_size();
+    std::vector<int> cnt(1, (int)mine.size()), cnts;
+    p2p_allgather_ints(cnt, cnts);
+    int mx = 1;
+    for (int c : cnts) mx = std::max(mx, c);
+    std::vector<int> pad(mine), flat;
+    pad.resize((size_t)mx, 0);
+    p2p_allgather_ints(pad, flat);
+    all.assign(nr, std::vector<int>());
+    for (int q = 0; q < nr; ++q) all[q].assign(flat.begin() + (size_t)q * mx, flat.begin() + (size_t)q * mx + cnts[q]);
+}
+
+// M: this rank's rows (owned + extra rows behind them) with GLOBAL column numbers
+static HaloPlan* upload_slab(DevCSR& d, const dCSRmat& M, const std::vector<int>& coff, int rank, bool pattern)
+{
+    LocalCSR loc;
+    loc.rows = M.row;
+    loc.ia.assign(M.IA, M.IA + M.row + 1);
+    if (loc.ia[0] != 0) fail(ERROR_DATA_STRUCTURE, "slab operator: IA[0] != 0");
+    const size_t nnz = (size_t)loc.ia[M.row];
+    loc.ja.assign(M.JA, M.JA + nnz);
+    if (!pattern && M.val) loc.val.assign(M.val, M.val + nnz);
+    for (int c : loc.ja)
+        if (c < 0 || c >= M.col) fail(ERROR_DATA_STRUCTURE, "slab operator: column %d outside [0, %d)", c, M.col);
+    dist_renumber(loc, M.col, coff, rank);
+    const int nloc_cols = coff.empty() ? -1 : coff[rank + 1] - coff[rank];
+    csr_upload(d, loc.rows, loc.cols, (long long)nnz, loc.ia.data(), loc.ja.data(),
+               loc.val.empty() ? nullptr : loc.val.data(), pattern, nloc_cols);
+    if (coff.empty()) return nullptr;
+    // what my peers gather from my owned columns: their ghost lists, all-gathered (collective)
+    std::vector<std::vector<int>> ghosts_of, send(comm_size());
+    allgather_lists(loc.ghosts, ghosts_of);
+    const int c0 = coff[rank], c1 = coff[rank + 1];
+    for (int q = 0; q < comm_size(); ++q) {
+        if (q == rank) continue;
+        const std::vector<int>& g = ghosts_of[q];
+        auto b = std::lower_bound(g.begin(), g.end(), c0), e = std::lower_bound(g.begin(), g.end(), c1);
+        for (auto it = b; it != e; ++it) send[q].push_back(*it - c0);
+    }
+    HaloPlan* h = plan_from_send_lists(coff, loc, rank, send);
+    d.halo      = h;
+    d.nghost    = h->nghost;
+    return h;
+}
+
+Amg* dist_amg_upload_slabs(int nlev, const fasp_cuda_slab_level* sl, const int* tail_off, AMG_data* tail,
+                           AMG_param* param)
+{
+    ensure_init();
+    if (!comm_active()) fail(ERROR_INPUT_PAR, "slab hierarchy: no communicator (fasp_cuda_comm_init first)");
+    const int rank = comm_rank(), nr = comm_size();
+    if (nlev < 1 || !sl || !tail || !tail_off) fail(ERROR_INPUT_PAR, "slab hierarchy: nlev = %d / null argument", nlev);
+    const int nt = tail[0].num_levels;
+    const int nl = nlev + nt;
+    if (nt < 1 || nl > MAX_AMG_LVL) fail(ERROR_DATA_STRUCTURE, "slab hierarchy: %d + %d levels", nlev, nt);
+    if (param->smoother != SMOOTHER_JACOBI && param->smoother != SMOOTHER_L1DIAG && param->smoother != SMOOTHER_POLY)
+        fail(ERROR_AMG_SMOOTH_TYPE, "multi-GPU cycle: smoother %d not supported (Jacobi 1, poly 9, L1 10)",
+             (int)param->smoother);
+    if (param->cycle_type == AMLI_CYCLE || param->cycle_type == NL_AMLI_CYCLE)
+        fail(ERROR_INPUT_PAR, "AMLI cycles are not on the device path");
+    const int lrep = nlev;
+    std::vector<std::vector<int>> off(nlev + 1);
+    for (int l = 0; l < nlev; ++l) off[l].assign(sl[l].row_off, sl[l].row_off + nr + 1);
+    off[nlev].assign(tail_off, tail_off + nr + 1);
+    for (int l = 0; l <= nlev; ++l) {
+        const int n_glob = (l < nlev) ? sl[l].A.col : tail[0].A.row;
+        if (off[l][0] != 0 || off[l][nr] != n_glob) fail(ERROR_DATA_STRUCTURE, "slab hierarchy: partition of level %d", l);
+        for (int r = 0; r < nr; ++r)
+            if (off[l][r + 1] < off[l][r]) fail(ERROR_DATA_STRUCTURE, "slab hierarchy: partition of level %d", l);
+    }
+    const std::vector<int> none;
+    Amg* h = new Amg();
+    try {
+        amg_set_params(*h, param);
+        h->nl   = nl;
+        h->dist = true;
+        h->off0 = off[0];
+        h->lv.resize(nl);
+        const bool ua        = (param->AMG_type == UA_AMG);
+        const bool redundant = ctx().opt.ghost_redundant != 0;
+        for (int l = 0; l < nl; ++l) {
+            Level& L = h->lv[l];
+            if (l < lrep) {
+                const fasp_cuda_slab_level& S = sl[l];
+                const int n_own  = off[l][rank + 1] - off[l][rank];
+                const int nc_own = off[l + 1][rank + 1] - off[l + 1][rank];
+                const bool next_dist = (l + 1 < lrep);
+                if (S.A.row != n_own) fail(ERROR_DATA_STRUCTURE, "slab level %d: A has %d rows, the partition says %d", l, S.A.row, n_own);
+                L.dist    = true;
+                L.nglobal = S.A.col;
+                L.row0    = off[l][rank];
+                L.n       = n_own;
+                L.hA      = upload_slab(L.A, S.A, off[l], rank, false);
+                int ghost = L.A.nghost;
+                // the extra rows must be exactly the ghost rows the cycle expects (same count on this rank); they are
+                // used only when the option is on AND the host supplied them
+                L.r_ext = redundant && next_dist && S.n_rext > 0;
+                L.p_ext = redundant && S.n_pext > 0;
+                if (S.P.row != n_own + S.n_pext || S.R.row != nc_own + S.n_rext)
+                    fail(ERROR_DATA_STRUCTURE, "slab level %d: P / R row counts do not match owned + extra rows", l);
+                if (S.n_pext != 0 && S.n_pext != L.A.nghost)
+                    fail(ERROR_DATA_STRUCTURE, "slab level %d: %d extra rows of P, A has %d ghost columns", l, S.n_pext, L.A.nghost);
+                dCSRmat Rm = S.R, Pm = S.P;
+                if (!L.r_ext) Rm.row = nc_own, Rm.nnz = Rm.IA[nc_own];
+                if (!L.p_ext) Pm.row = n_own, Pm.nnz = Pm.IA[n_own];
+                L.hR = upload_slab(L.R, Rm, off[l], rank, ua);
+                if (L.R.nghost > ghost) ghost = L.R.nghost;
+                L.hP = upload_slab(L.P, Pm, next_dist ? off[l + 1] : none, rank, ua);
+                if (l > 0 && h->lv[l - 1].P.nghost > ghost) ghost = h->lv[l - 1].P.nghost;
+                L.cap = L.n + ghost;
+                if (!next_dist) {
+                    L.gcounts.resize(nr);
+                    L.gdispls.resize(nr);
+                    for (int r = 0; r < nr; ++r) {
+                        L.gdispls[r] = (size_t)off[l + 1][r];
+                        L.gcounts[r] = (size_t)(off[l + 1][r + 1] - off[l + 1][r]);
+                    }
+                }
+                amg_level_smoother_data(*h, L, nullptr);
+            } else {
+                const AMG_data& T = tail[l - lrep];
+                const dCSRmat&  A = T.A;
+                L.nglobal         = A.row;
+                csr_upload(L.A, A.row, A.col, A.nnz, A.IA, A.JA, A.val);
+                L.n = A.row;
+                if (l < nl - 1) {
+                    csr_upload(L.P, T.P.row, T.P.col, T.P.nnz, T.P.IA, T.P.JA, T.P.val, ua);
+                    csr_upload(L.R, T.R.row, T.R.col, T.R.nnz, T.R.IA, T.R.JA, T.R.val, ua);
+                    amg_level_smoother_data(*h, L, &A);
+                }
+            }
+            finish_level(*h, L, l, lrep, redundant);
+            h->bytes += L.A.bytes + L.P.bytes + L.R.bytes;
+        }
+        // a slab level whose R carries the ghost rows of the next level: their count must be that level's ghost count
+        for (int l = 0; l + 1 < lrep; ++l)
+            if (h->lv[l].r_ext && sl[l].n_rext != h->lv[l + 1].A.nghost)
+                fail(ERROR_DATA_STRUCTURE, "slab level %d: %d extra rows of R, A_%d has %d ghost columns", l, sl[l].n_rext,
+                     l + 1, h->lv[l + 1].A.nghost);
+        h->scal = dalloc<double>(4);
+        FC_CUDA(cudaMemsetAsync(h->scal, 0, 4 * sizeof(double), ctx().stream));
+        amg_setup_coarse(*h);
         FC_CUDA(cudaStreamSynchronize(ctx().stream));
     } catch (...) {
         amg_free(h);

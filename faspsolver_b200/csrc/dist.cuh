@@ -46,7 +46,12 @@ void dist_send_lists(const dCSRmat& A, const std::vector<int>& roff, const std::
 // ghost columns (global, ascending) of every rank's row slab of a square level operator
 void dist_ghost_lists(const dCSRmat& A, const std::vector<int>& off, std::vector<std::vector<int>>& ghosts);
 
+void dist_renumber(LocalCSR& out, int global_cols, const std::vector<int>& coff, int rank);
+
 // Upload: levels with >= agg_rows global rows are partitioned, the rest replicated.
 Amg* dist_amg_upload(AMG_data* mgl, AMG_param* param, int agg_rows);
+// The same from per-rank slabs with global column numbers (nlev partitioned levels) + the replicated rest
+Amg* dist_amg_upload_slabs(int nlev, const fasp_cuda_slab_level* sl, const int* tail_off, AMG_data* tail,
+                           AMG_param* param);
 
 } // namespace fc

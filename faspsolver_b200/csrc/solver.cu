@@ -76,6 +76,31 @@ fasp_cuda_solver_s* solver_create_dist(AMG_data* mgl, AMG_param* amgparam, int a
     return s;
 }
 
+fasp_cuda_solver_s* solver_create_dist_slabs(int nlev, const fasp_cuda_slab_level* sl, const int* tail_off,
+                                             AMG_data* tail, AMG_param* amgparam)
+{
+    ensure_init();
+    fasp_cuda_solver_s* s = new fasp_cuda_solver_s();
+    try {
+        AMG_param p = *amgparam;
+        p.tol       = 1e-6;
+        s->amg      = dist_amg_upload_slabs(nlev, sl, tail_off, tail, &p);
+        s->n        = (size_t)s->amg->lv[0].n;
+        const size_t cap = (size_t)s->amg->lv[0].cap + 8;
+        s->d_b      = dalloc<double>(cap);
+        s->d_x      = dalloc<double>(cap);
+        if (p2p_active()) {
+            p2p_register(s->d_x, sizeof(double) * cap);
+            s->x_registered = true;
+        }
+        FC_CUDA(cudaMallocHost(&s->pin, sizeof(double) * 2 * s->n));
+    } catch (...) {
+        solver_destroy(s);
+        throw;
+    }
+    return s;
+}
+
 fasp_cuda_solver_s* solver_create_bsr(AMG_data_bsr* mgl, AMG_param* amgparam)
 {
     ensure_init();

@@ -57,6 +57,8 @@ void      require_host_fasp();
 fasp_cuda_solver_s* solver_create_csr(AMG_data* mgl, AMG_param* amgparam);
 fasp_cuda_solver_s* solver_create_bsr(AMG_data_bsr* mgl, AMG_param* amgparam);
 fasp_cuda_solver_s* solver_create_dist(AMG_data* mgl, AMG_param* amgparam, int agg_rows);
+fasp_cuda_solver_s* solver_create_dist_slabs(int nlev, const fasp_cuda_slab_level* sl, const int* tail_off,
+                                             AMG_data* tail, AMG_param* amgparam);
 void                solver_destroy(fasp_cuda_solver_s* s);
 int    solver_solve_dev(fasp_cuda_solver_s* s, const double* b_dev, double* x_dev, ITS_param* it);
 int    solver_solve_host(fasp_cuda_solver_s* s, const double* b, double* x, ITS_param* it);

@@ -29,6 +29,7 @@ PAIRWISE, VMB = 1, 2
 V_CYCLE, W_CYCLE, AMLI_CYCLE, NL_AMLI_CYCLE, VW_CYCLE, WV_CYCLE = 1, 2, 3, 4, 12, 21
 SMOOTHER_JACOBI, SMOOTHER_GS, SMOOTHER_SGS, SMOOTHER_POLY, SMOOTHER_L1DIAG = 1, 2, 3, 9, 10
 COARSE_RS = 1
+MIN_CDOF = 20   # fasp_const.h:260
 INTERP_DIR = 1
 ON, OFF = 1, 0
 
@@ -152,6 +153,11 @@ class mxv_matfree(C.Structure):
 
 
 MAT_CSR, MAT_BSR = 1, 2
+
+
+class fasp_cuda_slab_level(C.Structure):
+    """include/fasp_cuda.h: one row-partitioned level handed to fasp_cuda_dist_krylov_amg_create_slabs"""
+    _fields_ = [("A", dCSRmat), ("P", dCSRmat), ("R", dCSRmat), ("row_off", PINT), ("n_pext", INT), ("n_rext", INT)]
 
 
 # ---- numpy <-> struct helpers ------------------------------------------------------------

@@ -65,6 +65,16 @@ def allreduce_max(x: float) -> float:
     return float(t[0])
 
 
+def allreduce_sum(x: float) -> float:
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        return x
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t[0])
+
+
 def barrier():
     import torch.distributed as dist
     if dist.is_initialized():
@@ -82,6 +92,22 @@ class DistSolver(api.KrylovAmgSolver):
         b, e = C.c_int(0), C.c_int(0)
         api.check(L.fasp_cuda_dist_row_range(self.h, C.byref(b), C.byref(e)))
         self.row0, self.row1 = b.value, e.value
+
+
+class SlabSolver(api.KrylovAmgSolver):
+    """The same solver built from a slabsetup.SlabHierarchy (no global matrix on any rank)."""
+
+    def __init__(self, sh):
+        L = api.lib()
+        self.h = sh.create_solver()
+        b, e = C.c_int(0), C.c_int(0)
+        api.check(L.fasp_cuda_dist_row_range(self.h, C.byref(b), C.byref(e)))
+        self.row0, self.row1 = b.value, e.value
+
+
+def plane_partition(n_planes, world):
+    """z-planes per rank, as even as possible; returns plane offsets (world + 1)."""
+    return [(n_planes * r) // world for r in range(world + 1)]
 
 
 # ---------------------------------------------------------------------------------------

@@ -11,8 +11,10 @@ import numpy as np
 from .fasp_types import BSR, CSR
 
 
-def _stencil_csr(nx, ny, nz, offsets, coeffs, chunk_planes=16):
+def _stencil_csr(nx, ny, nz, offsets, coeffs, chunk_planes=16, zrange=None):
     """CSR of a constant-coefficient stencil on an nx*ny*nz grid.
+
+    zrange = (z0, z1): only the rows of the planes z0 <= z < z1 (a z-slab, GLOBAL column numbers).
 
     offsets: list of (dx, dy, dz) sorted so that the linear offset dx + nx*(dy + ny*dz) ascends.
     coeffs : one value per offset. Built plane-chunk by plane-chunk to bound peak memory.
@@ -22,12 +24,14 @@ def _stencil_csr(nx, ny, nz, offsets, coeffs, chunk_planes=16):
     lin = offsets[:, 0] + nx * (offsets[:, 1] + ny * offsets[:, 2])
     assert np.all(np.diff(lin) > 0), "offsets must be sorted by linear offset"
     N = nx * ny * nz
-    counts = np.empty(N, dtype=np.int32)
+    zlo, zhi = zrange if zrange is not None else (0, nz)
+    row0, nrows = zlo * nx * ny, (zhi - zlo) * nx * ny
+    counts = np.empty(nrows, dtype=np.int32)
     ja_parts, va_parts = [], []
     ix = np.arange(nx, dtype=np.int64)
     iy = np.arange(ny, dtype=np.int64)
-    for z0 in range(0, nz, chunk_planes):
-        z1 = min(nz, z0 + chunk_planes)
+    for z0 in range(zlo, zhi, chunk_planes):
+        z1 = min(zhi, z0 + chunk_planes)
         iz = np.arange(z0, z1, dtype=np.int64)
         Z, Y, X = np.meshgrid(iz, iy, ix, indexing="ij")
         X, Y, Z = X.ravel(), Y.ravel(), Z.ravel()
@@ -40,14 +44,14 @@ def _stencil_csr(nx, ny, nz, offsets, coeffs, chunk_planes=16):
         cols = (base[:, None] + lin[None, :]).astype(np.int32)
         ja_parts.append(cols[valid])
         va_parts.append(np.broadcast_to(coeffs[None, :], valid.shape)[valid])
-        counts[base[0]:base[0] + m] = valid.sum(axis=1, dtype=np.int32)
-    ia = np.zeros(N + 1, dtype=np.int64)
+        counts[base[0] - row0:base[0] - row0 + m] = valid.sum(axis=1, dtype=np.int32)
+    ia = np.zeros(nrows + 1, dtype=np.int64)
     np.cumsum(counts, out=ia[1:])
-    assert ia[-1] < 2 ** 31, "matrix exceeds FASP's 32-bit INT (SURVEY.md finding 4)"
-    return CSR(N, N, ia.astype(np.int32), np.concatenate(ja_parts), np.concatenate(va_parts))
+    assert ia[-1] < 2 ** 31 and N < 2 ** 31, "matrix exceeds FASP's 32-bit INT (SURVEY.md finding 4)"
+    return CSR(nrows, N, ia.astype(np.int32), np.concatenate(ja_parts), np.concatenate(va_parts))
 
 
-def poisson7(n, scaled=True, ny=None, nz=None):
+def poisson7(n, scaled=True, ny=None, nz=None, zrange=None):
     """3-D 7-point Poisson on n^3 interior nodes: diag 6 h^-2, off -h^-2, h = 1/(n+1)
     (entries as in test/src/FdmPoisson.c:518-541; ordering as the survey probes)."""
     ny = ny or n
@@ -55,16 +59,16 @@ def poisson7(n, scaled=True, ny=None, nz=None):
     s = float((n + 1) ** 2) if scaled else 1.0
     offs = [(0, 0, -1), (0, -1, 0), (-1, 0, 0), (0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]
     co = [-s, -s, -s, 6 * s, -s, -s, -s]
-    return _stencil_csr(n, ny, nz, offs, co)
+    return _stencil_csr(n, ny, nz, offs, co, zrange=zrange)
 
 
-def poisson27(n, ny=None, nz=None):
-    """3-D 27-point M-matrix: diag 26, all 26 neighbours -1 (config 3)."""
+def poisson27(n, ny=None, nz=None, zrange=None):
+    """3-D 27-point M-matrix: diag 26, all 26 neighbours -1 (config 3). zrange: rows of a z-slab only."""
     ny = ny or n
     nz = nz or n
     offs = [(dx, dy, dz) for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
     co = [26.0 if o == (0, 0, 0) else -1.0 for o in offs]
-    return _stencil_csr(n, ny, nz, offs, co)
+    return _stencil_csr(n, ny, nz, offs, co, zrange=zrange)
 
 
 def convdiff7(n, peclet=(0.5, 0.25, 0.125)):

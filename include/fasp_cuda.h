@@ -364,6 +364,25 @@ int fasp_cuda_comm_peer_memory(void);
  * with fasp_cuda_krylov_amg_solve / _solve_dev / _destroy; b and x are the rank's LOCAL slices.    */
 fasp_cuda_solver* fasp_cuda_dist_krylov_amg_create(AMG_data* mgl, AMG_param* amgparam, INT agg_rows);
 INT fasp_cuda_dist_row_range(const fasp_cuda_solver* s, INT* row_begin, INT* row_end);
+/* The same solver from per-rank SLABS: no rank holds a global matrix, so the fine levels may exceed what one
+ * dCSRmat can address (INT is 32-bit, fasp.h:72: the 27-point 512^3 system has 3.6 G nonzeros). Level l < nlev:
+ *   A  this rank's rows [row_off[rank], row_off[rank+1]) of A_l, GLOBAL column numbers, col = global size;
+ *   P  the same rows of P_l (global coarse columns), optionally followed by n_pext extra rows = the rows of P_l
+ *      for the ghost columns of the A slab, ascending (the cycle then updates the ghosts of x_l redundantly
+ *      instead of exchanging them; n_pext = 0: not supplied);
+ *   R  this rank's rows of R_l = P_l^T (rows [row_off_{l+1}[rank], ...), global fine columns), optionally
+ *      followed by n_rext extra rows = the rows for the ghost columns of the A_{l+1} slab.
+ * tail_row_off partitions the first replicated level; `tail` is an ordinary FASP hierarchy (fasp_amg_setup_*)
+ * whose level-0 matrix is that level, identical on every rank. Built by FASP's own per-level routines on each
+ * slab + a distributed Galerkin product: faspsolver_b200/slabsetup.py, DESIGN.md §6.                        */
+typedef struct fasp_cuda_slab_level {
+    dCSRmat    A, P, R;
+    const INT* row_off; /* nranks + 1 */
+    INT        n_pext, n_rext;
+} fasp_cuda_slab_level;
+fasp_cuda_solver* fasp_cuda_dist_krylov_amg_create_slabs(INT nlev, const fasp_cuda_slab_level* levels,
+                                                         const INT* tail_row_off, AMG_data* tail,
+                                                         AMG_param* amgparam);
 /* Host-only (no GPU, no communicator): the local slab of a square operator for `rank` of `nranks`:
  * local ia/ja (columns renumbered [owned | ghosts]), the ghosts' global columns, and per peer the
  * owned local indices that peer needs (send_idx concatenated by peer, send_counts[nranks]).

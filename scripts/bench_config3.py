@@ -1,0 +1,172 @@
+#!/usr/bin/env python
+"""BASELINE configs[2]: 3-D 27-point Poisson n^3 (n = 512: 134 M rows, 3.6 G nonzeros), AMG-PCG, rows partitioned
+in z-slabs over the ranks. No rank holds the global matrix: every rank generates its slab, the hierarchy is
+built slab by slab with FASP's own per-level routines (faspsolver_b200/slabsetup.py), the solve is
+fasp_cuda_krylov_amg_solve on the slab solver. Launch with torchrun (one rank per GPU); N = 1 runs the ordinary
+one-GPU path on the same (one-slab = FASP's own) hierarchy when the matrix fits one dCSRmat.
+
+    python -m torch.distributed.run --nproc-per-node 8 ... scripts/bench_config3.py --n 512
+Prints one JSON line on rank 0."""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from faspsolver_b200 import api, fasp_types as T, multigpu as MG, problems as PB, slabsetup as SS  # noqa: E402
+import bench as B  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--stencil", type=int, default=27)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--agg-rows", type=int, default=8000)
+    ap.add_argument("--opt", action="append", default=[])
+    ap.add_argument("--profile", type=int, default=1)
+    args = ap.parse_args()
+    rank, world, local = MG.init_comm()
+    L = api.lib()
+    for kv in args.opt:
+        k, v = kv.split("=")
+        api.check(L.fasp_cuda_set_option(k.encode(), float(v)))
+    log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
+    hf = B.host_fasp()
+    n = args.n
+    zoff = MG.plane_partition(n, world)
+    off = [z * n * n for z in zoff]
+    t = time.time()
+    gen = PB.poisson27 if args.stencil == 27 else PB.poisson7
+    A = gen(n, zrange=(zoff[rank], zoff[rank + 1]))
+    t_gen = time.time() - t
+    N = n ** 3
+    nloc = A.shape[0]
+    nnz_tot = MG.allreduce_sum(float(A.nnz))
+    log("[config3] %d-pt %d^3: %d rows, %.0f nnz; this rank %d rows / %d nnz (generated in %.1fs)" %
+        (args.stencil, n, N, nnz_tot, nloc, A.nnz, t_gen))
+    amg, it = B.amg_recipe(hf)
+    comm = SS.HostComm(rank, world)
+    t = time.time()
+    sh = SS.SlabHierarchy(hf, A, off, amg, comm, agg_rows=args.agg_rows, log=log)
+    t_setup = time.time() - t
+    t = time.time()
+    if world > 1:
+        solver = MG.SlabSolver(sh)
+    else:
+        mgl, amg_g = SS.assemble_mgl(hf, sh)
+        solver = api.KrylovAmgSolver(mgl, amg_g)
+    t_upload = time.time() - t
+    log("[config3] slab setup %.1fs (%d partitioned levels + %d replicated), upload %.1fs" %
+        (t_setup, len(sh.levels), sh.tail[0].num_levels, t_upload))
+    b_loc = np.ones(nloc)
+    zero = np.zeros(nloc)
+    x_buf = np.zeros(nloc)
+    api.pin_host(b_loc)
+    api.pin_host(x_buf)
+
+    def solve():
+        st, x = solver.solve(b_loc, zero, it, out=x_buf)
+        if st < 0:
+            raise RuntimeError("solve failed on rank %d: %d %s" % (rank, st, api.last_error()))
+        return st, x
+
+    for _ in range(args.warmup):
+        iters, _x = solve()
+    MG.barrier()
+    dev_ms, e2e_ms = [], []
+    for _ in range(args.steps):
+        MG.barrier()
+        iters, x_loc = solve()
+        dev_ms.append(MG.allreduce_max(solver.stat(2)))
+        e2e_ms.append(MG.allreduce_max(solver.stat(4)))
+    relres = solver.stat(1)
+    # true residual, slab by slab: the ghost entries of x come from their owners
+    ghosts = SS.ghost_columns(A, off[rank], off[rank + 1])
+    xg = SS.fetch_entries(comm, x_loc, np.asarray(off), ghosts)
+    own0, own1 = off[rank], off[rank + 1]
+    rr_loc = 0.0
+    for a0 in range(0, nloc, 1 << 21):      # row chunks: bounded host memory at 512^3
+        a1 = min(nloc, a0 + (1 << 21))
+        k0, k1 = int(A.ia[a0]), int(A.ia[a1])
+        ja = A.ja[k0:k1].astype(np.int64)
+        mine = (ja >= own0) & (ja < own1)
+        xa = np.empty(k1 - k0)
+        xa[mine] = x_loc[ja[mine] - own0]
+        xa[~mine] = xg[np.searchsorted(ghosts, ja[~mine])]
+        rows = np.repeat(np.arange(a1 - a0), np.diff(A.ia[a0:a1 + 1]))
+        r = b_loc[a0:a1] - np.bincount(rows, weights=A.val[k0:k1] * xa, minlength=a1 - a0)
+        rr_loc += float(r @ r)
+    rr = MG.allreduce_sum(rr_loc)
+    bb = MG.allreduce_sum(float(b_loc @ b_loc))
+    true_rel = float(np.sqrt(rr / bb))
+    # per-kernel profile of one more solve (CUDA events around every launch, graphs off)
+    roofline, levels = None, None
+    if args.profile:
+        L.fasp_cuda_set_option(b"profile", 1.0)
+        L.fasp_cuda_profile_dump(None, 0)
+        solve()
+        buf = C.create_string_buffer(64 << 20)
+        L.fasp_cuda_profile_dump(buf, len(buf))
+        L.fasp_cuda_set_option(b"profile", 0.0)
+        recs = [ln.split() for ln in buf.value.decode().splitlines()]
+        recs = [(int(k), int(r_), int(z_), float(ms_), float(by)) for k, r_, z_, ms_, by in recs]
+        mat = [x for x in recs if x[0] < 50]
+        groups = {}
+        for x in mat:
+            groups.setdefault(x[:3], []).append(x[3])
+        med = {k: float(np.percentile(v, 90)) for k, v in groups.items()}
+        mat = [x for x in mat if x[3] >= 0.25 * med[x[:3]]]
+        lv = {}
+        for k, r_, z_, ms_, by in mat:
+            e = lv.setdefault((r_, z_), [0, 0.0, 0.0])
+            e[0] += 1; e[1] += ms_; e[2] += by
+        levels = [{"rows": r_, "nnz": z_, "launches": c, "ms": ms_, "GBps": by / ms_ * 1e-6 if ms_ else 0}
+                  for (r_, z_), (c, ms_, by) in sorted(lv.items(), key=lambda kv: -kv[0][1])][:12]
+        top = levels[0]
+        peak, src = B.peaks()
+        comm_recs = [x for x in recs if x[0] >= 400]
+        roofline = {"bound": "hbm", "kernel": "csr_pipe_kernel on rank 0's level-0 slab (%d rows, %d nnz)" % (top["rows"], top["nnz"]),
+                    "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": top["GBps"] / peak,
+                    "frac_of_nominal_8000": top["GBps"] / 8000.0, "peak_source": src,
+                    "matrix_kernel_ms": sum(x[3] for x in mat), "comm_ms_profiled": sum(x[3] for x in comm_recs),
+                    "comm_ops": len(comm_recs)}
+    if rank == 0:
+        ms = float(np.mean(dev_ms))
+        out = {"metric": "amg_pcg_solve_time_poisson3d_%dpt" % args.stencil, "value": ms, "unit": "ms", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
+               "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "configs[2]: 3D %d-point Poisson %d^3 (%d rows, %.0f nnz), rhs=1, AMG-PCG tol 1e-8, "
+                                      "classical RS built slab by slab with FASP's per-level routines + distributed Galerkin "
+                                      "product, V(1,1) L1-Jacobi; z-slabs over %d GPUs" % (args.stencil, n, N, nnz_tot, world),
+                          "iterations": int(iters), "final_relres": relres, "true_relres": true_rel,
+                          "partitioned_levels": len(sh.levels), "replicated_levels": int(sh.tail[0].num_levels),
+                          "level_rows": [int(lv_.off[-1]) for lv_ in sh.levels] + [int(sh.tail[k].A.row) for k in range(sh.tail[0].num_levels)],
+                          "setup_s_host": t_setup, "upload_s": t_upload, "agg_rows": args.agg_rows},
+               "ms_per_iteration": ms / max(int(iters), 1),
+               "e2e": {"value": float(np.mean(e2e_ms)), "unit": "ms", "h2d_bytes_per_step": int(16 * nloc),
+                       "d2h_bytes_per_step": int(8 * nloc)},
+               "roofline": roofline, "levels": levels}
+        print(json.dumps(out), flush=True)
+        if not true_rel <= 1e-8 * 1.001:
+            raise RuntimeError("solution misses the tolerance: %g" % true_rel)
+    MG.barrier()
+    api.unpin_host(b_loc)
+    api.unpin_host(x_buf)
+    solver.close()
+    sh.close()
+    if world > 1:
+        L.fasp_cuda_comm_finalize()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,13 +1,15 @@
 #!/usr/bin/env bash
-# A/B on one box: the round-1 library (worktree _ab/r01, commit d7c4be1) against HEAD, same bench, interleaved
+# A/B on one box: stream priority on/off at HEAD, and the round-1 library (worktree _ab/r01, commit d7c4be1)
 set -u
 cd "$(dirname "$0")/.."
-O=$PWD/gpurun_out/r02ab
+O=$PWD/gpurun_out/r02ab2
 mkdir -p $O
 export PYTHONUNBUFFERED=1
-for i in 1 2; do
-  (cd _ab/r01 && timeout 400 python bench.py --steps 10 --warmup 3 > $O/old_$i.json 2> $O/old_$i.log); echo "old $i rc=$?"
-  python scripts/show_bench.py $O/old_$i.json | head -8
-  timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --extras 0 > $O/new_$i.json 2> $O/new_$i.log; echo "new $i rc=$?"
-  python scripts/show_bench.py $O/new_$i.json | head -8
-done
+run() { # name, env
+  env $2 timeout 400 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --extras 0 > $O/$1.json 2> $O/$1.log; echo "$1 rc=$?"
+  python scripts/show_bench.py $O/$1.json 2>/dev/null | sed -n 1,6p
+}
+run prio1_a FASP_CUDA_STREAM_PRIO=1
+run prio0_a FASP_CUDA_STREAM_PRIO=0
+run prio1_b FASP_CUDA_STREAM_PRIO=1
+run prio0_b FASP_CUDA_STREAM_PRIO=0

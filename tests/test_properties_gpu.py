@@ -134,3 +134,19 @@ def test_repeated_host_solves_with_fresh_and_pinned_buffers(gpu, ref):
         s.close()
     finally:
         ref.amg_free(mgl, amg)
+
+
+def test_amg_pcg_27pt_64_matches_sequential_reference(gpu, ref):
+    """BASELINE configs[2]'s operator (27-point, diag 26 / off -1) at a size the sequential oracle finishes in
+    seconds: same iteration count (+-1), true residual <= tol, solution within 1e-8 of the reference's."""
+    A = PB.poisson27(64)
+    n = A.shape[0]
+    b = np.ones(n)
+    it = ref.its_param(itsolver_type=T.SOLVER_CG, tol=1e-8, maxit=100, print_level=0)
+    amg = ref.amg_param(print_level=0, smoother=T.SMOOTHER_L1DIAG)
+    st, x = api.fasp_cuda_solver_dcsr_krylov_amg(A, b, np.zeros(n), it, amg)
+    amg_r = ref.amg_param(print_level=0, smoother=T.SMOOTHER_L1DIAG)
+    st_ref, x_ref = ref.krylov_amg(A, b, np.zeros(n), it, amg_r)
+    assert st > 0 and abs(st - st_ref) <= 1, (st, st_ref, api.last_error())
+    assert np.linalg.norm(b - A.to_scipy() @ x) / np.linalg.norm(b) <= 1e-8
+    assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) <= 1e-8
