@@ -103,6 +103,7 @@ bsr_pipe_kernel(const BsrView A, const BsrArgs a, const int nblk, const int nsta
         const bool  valid  = il < m.nrows;
         const int   I      = m.r0 + il;
         double      acc    = 0.0;
+        double      drow[MODE == BSR_JACOBI ? NB : 1];
         if (valid) {
             // where this block row's blocks live: staged slice or (oversized row) global memory
             const double* vbase;
@@ -121,6 +122,11 @@ bsr_pipe_kernel(const BsrView A, const BsrArgs a, const int nblk, const int nsta
                 jbase = A.ja;
             }
             const size_t row = (size_t)I * NB + i;
+            if (MODE == BSR_JACOBI) {   // this thread's row of Dinv_I, fetched now: its latency hides behind the gathers
+                const double* D = a.diaginv + (size_t)I * NB2 + i * NB;
+#pragma unroll
+                for (int j = 0; j < NB; ++j) drow[j] = __ldg(D + j);
+            }
             if (MODE == BSR_MXV) acc = 0.0;
             else if (MODE == BSR_AXPY) {
                 const double y0 = a.y[row];
@@ -166,17 +172,16 @@ bsr_pipe_kernel(const BsrView A, const BsrArgs a, const int nblk, const int nsta
             s_tmp[tid] = acc;
             __syncthreads();
             if (valid) {
-                const double* D = a.diaginv + (size_t)I * NB2 + i * NB;
                 const double* t = s_tmp + il * NB;
                 if (NB <= 7) {
-                    double e = __dmul_rn(D[0], t[0]);
+                    double e = __dmul_rn(drow[0], t[0]);
 #pragma unroll
-                    for (int j = 1; j < NB; ++j) e = __dadd_rn(e, __dmul_rn(D[j], t[j]));
+                    for (int j = 1; j < NB; ++j) e = __dadd_rn(e, __dmul_rn(drow[j], t[j]));
                     out = e;
                 } else {
                     double e = 0.0;
 #pragma unroll
-                    for (int j = 0; j < NB; ++j) e = __dadd_rn(e, __dmul_rn(D[j], t[j]));
+                    for (int j = 0; j < NB; ++j) e = __dadd_rn(e, __dmul_rn(drow[j], t[j]));
                     out = e;
                 }
             }

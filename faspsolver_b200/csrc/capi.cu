@@ -166,6 +166,7 @@ static int* option_slot(const char* key)
     if (!strcmp(key, "host_register")) return &o.host_register;
     if (!strcmp(key, "rowwise_max")) return &o.rowwise_max;
     if (!strcmp(key, "gather16_min_avg")) return &o.gather16_min_avg;
+    if (!strcmp(key, "two_phase_mask")) return &o.two_phase_mask;
     if (!strcmp(key, "wide_threads")) return &o.wide_threads;
     if (!strcmp(key, "vec_lpr")) return &o.vec_lpr;
     if (!strcmp(key, "gs_multicolor")) return &o.gs_multicolor;

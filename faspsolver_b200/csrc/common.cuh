@@ -64,6 +64,9 @@ struct Options {
     int    pipe_tpb         = 128; // its threads per CTA = max rows per row block (64/128/256)
     int    wide_threads     = 400000; // long rows: double the lanes per row (up to 256 = csr_wide_kernel) while
                                       // rows x lanes stays below this and a lane keeps >= 8 entries
+    int    two_phase_mask   = 0x6;  // pipelined kernel: bit MODE set = gather rounds in two enforced phases (spmv.cu).
+                                   // Default: y += a A x (transfer operators) and r = b - A x, where it measured faster
+                                   // (profiles/r02_two_phase_sweep.txt); the L1 / Jacobi sweeps and y = A x lose with it
     int    gather16_min_avg = 6;   // pipelined kernel: rows averaging >= this use the 16-deep gather variant (0 = never)
     int    rowwise_max      = 64;  // blocks averaging <= this many nonzeros per row: one thread per row
     int    vec_lpr          = 0;   // > 0: force this many lanes per row in the vector kernel

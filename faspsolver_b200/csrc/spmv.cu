@@ -68,48 +68,68 @@ __device__ __forceinline__ double ld_stream_f64(const double* p)
 // `acc` is sum_k a_ik x_k for the SpMV-like modes. For the smoother modes with exact==true it
 // is already t_i = b_i - sum (accumulated by subtraction, as the CPU does); with
 // exact==false it is the plain sum and t_i is formed here.
+// The vector operands of the epilogue, fetched BEFORE the gather rounds of the row: read where they are used,
+// they are one more dependent DRAM access at the end of every row (ncu, L1 sweep: 18 % of all stall samples sat
+// on the test of the freshly loaded l1 entry, profiles/r02_l1_sweep_scheduling.txt).
+struct EpiPre {
+    double p0, p1, p2;
+};
+template <int MODE>
+__device__ __forceinline__ EpiPre epi_prefetch(const CsrView& A, const CsrArgs& a, int row, bool exact)
+{
+    EpiPre e{0.0, 0.0, 0.0};
+    if (MODE == CSR_AXPY) e.p0 = a.y[row];
+    else if (MODE == CSR_RESID) e.p0 = a.b[row];
+    else if (MODE == CSR_RESID_DINV) e.p0 = a.b[row], e.p1 = A.dinv[row];
+    else if (MODE == CSR_JACOBI) e.p0 = exact ? 0.0 : a.b[row], e.p1 = A.diag[row], e.p2 = a.x[row];
+    else if (MODE == CSR_L1) e.p0 = exact ? 0.0 : a.b[row], e.p1 = A.l1[row], e.p2 = a.x[row];
+    else if (MODE == CSR_POLY1) e.p0 = a.x[row], e.p1 = A.dinv[row];
+    else if (MODE == CSR_POLYJ) e.p0 = a.b[row], e.p1 = A.dinv[row], e.p2 = a.x[row];
+    return e;
+}
+
 template <int MODE>
 __device__ __forceinline__ double row_epilogue(const CsrView& A, const CsrArgs& a, int row,
-                                               double acc, bool exact)
+                                               double acc, bool exact, const EpiPre& pre)
 {
     double out;
     if (MODE == CSR_MXV) {
         out = acc;
     } else if (MODE == CSR_AXPY) {
         // BlaSpmvCSR.c:509-590: alpha == 1 / -1 / general (temp*alpha added last)
-        const double y0 = a.y[row];
+        const double y0 = pre.p0;
         const double al = a.alpha_dev ? *a.alpha_dev : a.alpha;
         if (al == 1.0) out = __dadd_rn(y0, acc);
         else if (al == -1.0) out = __dsub_rn(y0, acc);
         else out = __dadd_rn(y0, __dmul_rn(acc, al));
     } else if (MODE == CSR_RESID || MODE == CSR_RESID_DINV) {
-        out = __dsub_rn(a.b[row], acc);
-        if (MODE == CSR_RESID_DINV) a.v0_out[row] = __dmul_rn(A.dinv[row], out);
+        out = __dsub_rn(pre.p0, acc);
+        if (MODE == CSR_RESID_DINV) a.v0_out[row] = __dmul_rn(pre.p1, out);
     } else if (MODE == CSR_JACOBI) {
         // ItrSmootherCSR.c:148-170
-        const double t = exact ? acc : __dsub_rn(a.b[row], acc);
-        const double d = A.diag[row];
-        const double u = a.x[row];
+        const double t = exact ? acc : __dsub_rn(pre.p0, acc);
+        const double d = pre.p1;
+        const double u = pre.p2;
         const double w = a.alpha;
         out = (fabs(d) > SMALLREAL)
                   ? __dadd_rn(__dmul_rn(1.0 - w, u), __ddiv_rn(__dmul_rn(w, t), d))
                   : u;
     } else if (MODE == CSR_L1) {
         // ItrSmootherCSR.c:1560-1574
-        const double t = exact ? acc : __dsub_rn(a.b[row], acc);
-        const double d = A.l1[row];
-        const double u = a.x[row];
+        const double t = exact ? acc : __dsub_rn(pre.p0, acc);
+        const double d = pre.p1;
+        const double u = pre.p2;
         out = (fabs(d) > SMALLREAL) ? __dadd_rn(u, __ddiv_rn(t, d)) : u;
     } else if (MODE == CSR_POLY1) {
         // ItrSmootherCSRpoly.c:572-583 : x = rbar ; v0 = k1 rbar ; v1 = k2 rbar - k3 Dinv (A rbar)
-        const double rb = a.x[row];
-        const double av = __dmul_rn(A.dinv[row], acc);
+        const double rb = pre.p0;
+        const double av = __dmul_rn(pre.p1, acc);
         a.v0_out[row]   = __dmul_rn(a.k1, rb);
         out             = __dsub_rn(__dmul_rn(a.k2, rb), __dmul_rn(a.k3, av));
         if (a.u_acc) a.u_acc[row] = __dadd_rn(a.u_acc[row], out);   // never used by FASP (ndeg>=2)
     } else { // CSR_POLYJ, ItrSmootherCSRpoly.c:588-608 : x = v1
-        const double v1 = a.x[row];
-        const double rb = __dmul_rn(__dsub_rn(a.b[row], acc), A.dinv[row]);
+        const double v1 = pre.p2;
+        const double rb = __dmul_rn(__dsub_rn(pre.p0, acc), pre.p1);
         out = __dadd_rn(__dadd_rn(v1, __dmul_rn(a.k5, __dsub_rn(v1, a.v0[row]))),
                         __dmul_rn(a.k4, rb));
         if (a.u_acc) a.u_acc[row] = __dadd_rn(a.u_acc[row], out);
@@ -151,7 +171,7 @@ struct PipeMeta {
     int r0, nrows, k0, n;
 };
 
-template <int MODE, bool PATTERN, int T, int UG>
+template <int MODE, bool PATTERN, int T, int UG, bool TP>
 __global__ void __launch_bounds__(T)
 csr_pipe_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, const int nstages,
                 const int strict, double* partials, unsigned int* ticket)
@@ -175,6 +195,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, const int 
     const int2* __restrict__ desc = A.blkdesc;   // desc[b] = {first row, ia[first row]}
     const double* __restrict__ x  = a.x;
     auto gx = [&](int col) { return __ldg(x + col); };
+    const int zero = (int)gridDim.y - 1;   // 0 (the grid is one-dimensional), but neither nvcc nor ptxas can fold it
 
     // thread 0 is the producer: one mbarrier arrival (+ the bulk-copy byte count) per stage use
     auto issue = [&](int blk, int s) {
@@ -233,14 +254,26 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, const int 
                     const int kb   = sia[tid + 1] - k0;
                     const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
                     double    acc  = ModeTraits<MODE>::smoother ? a.b[row] : 0.0;
+                    const EpiPre pre = epi_prefetch<MODE>(A, a, row, true);
                     constexpr int U = UG;   // gathers in flight per row thread
                     for (int kk = ka; kk < kb; kk += U) {
                         int    col[U];
                         double xv[U];
 #pragma unroll
                         for (int u = 0; u < U; ++u) col[u] = (kk + u < kb) ? sj[kk + u] : -1;
+                        // TP ("two phases"): all column indices out of shared memory, THEN the gathers back to back.
+                        // Left alone, ptxas interleaves the LDS and LDG of a round and, with six scoreboards for 32
+                        // loads, may make the sign test of one column index wait for an earlier gather: the L1 sweep
+                        // lost 10-17 % in one build with unchanged source (ncu: long-scoreboard 4.3 -> 6.3 per issue,
+                        // profiles/r02_l1_sweep_scheduling.txt). With TP every gather address carries a term that is
+                        // zero at run time but depends on every column index of the round. It costs the modes whose
+                        // natural schedule is good 3-7 %, so it is chosen per mode (option two_phase_mask).
+                        int any = 0;
 #pragma unroll
-                        for (int u = 0; u < U; ++u) xv[u] = (col[u] >= 0) ? gx(col[u]) : 0.0;
+                        for (int u = 0; u < U; ++u) any |= col[u];
+                        const int dep = TP ? (any & zero) : 0;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) xv[u] = (col[u] >= 0) ? gx(col[u] + dep) : 0.0;
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
                             const int k = kk + u;
@@ -250,7 +283,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, const int 
                             }
                         }
                     }
-                    const double out = row_epilogue<MODE>(A, a, row, acc, true);
+                    const double out = row_epilogue<MODE>(A, a, row, acc, true, pre);
                     if (want_dot) red_dot += out * a.red.dot_with[row];
                     if (want_n2) red_n2 += out * out;
                 }
@@ -265,8 +298,12 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, const int 
                         const int k = base + tid + e * T;
                         col[e]      = (k < n) ? sj[k] : -1;
                     }
+                    int any = 0;   // two phases, as in the row-wise path
 #pragma unroll
-                    for (int e = 0; e < EPT; ++e) xv[e] = (col[e] >= 0) ? gx(col[e]) : 0.0;
+                    for (int e = 0; e < EPT; ++e) any |= col[e];
+                    const int dep = TP ? (any & zero) : 0;
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) xv[e] = (col[e] >= 0) ? gx(col[e] + dep) : 0.0;
 #pragma unroll
                     for (int e = 0; e < EPT; ++e) {
                         const int k = base + tid + e * T;
@@ -279,8 +316,10 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, const int 
                 const bool valid = g < nrows;
                 double     part  = 0.0;
                 int        row   = r0;
+                EpiPre pre{0.0, 0.0, 0.0};
                 if (valid) {
                     row            = r0 + g;
+                    if (gl == 0) pre = epi_prefetch<MODE>(A, a, row, false);
                     const int ka   = sia[g] - k0;
                     const int kb   = sia[g + 1] - k0;
                     const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
@@ -290,7 +329,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, const int 
                 for (int off = lpr >> 1; off > 0; off >>= 1)
                     part += __shfl_xor_sync(0xffffffffu, part, off);
                 if (valid && gl == 0) {
-                    const double out = row_epilogue<MODE>(A, a, row, part, false);
+                    const double out = row_epilogue<MODE>(A, a, row, part, false, pre);
                     if (want_dot) red_dot += out * a.red.dot_with[row];
                     if (want_n2) red_n2 += out * out;
                 }
@@ -308,7 +347,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, const int 
                         const double p = PATTERN ? x[A.ja[k]] : __dmul_rn(A.val[k], x[A.ja[k]]);
                         acc = ModeTraits<MODE>::smoother ? __dsub_rn(acc, p) : __dadd_rn(acc, p);
                     }
-                    const double out = row_epilogue<MODE>(A, a, row, acc, true);
+                    const double out = row_epilogue<MODE>(A, a, row, acc, true, epi_prefetch<MODE>(A, a, row, true));
                     if (want_dot) red_dot += out * a.red.dot_with[row];
                     if (want_n2) red_n2 += out * out;
                 }
@@ -326,7 +365,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, const int 
                 if (tid == 0) {
                     double acc = 0.0;
                     for (int w = 0; w < T / 32; ++w) acc += s_red[w];
-                    const double out = row_epilogue<MODE>(A, a, row, acc, false);
+                    const double out = row_epilogue<MODE>(A, a, row, acc, false, epi_prefetch<MODE>(A, a, row, false));
                     if (want_dot) red_dot += out * a.red.dot_with[row];
                     if (want_n2) red_n2 += out * out;
                 }
@@ -373,10 +412,12 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, double* 
     const int*    __restrict__ ja  = A.ja;
     const double* __restrict__ val = A.val;
     double part = 0.0;
+    EpiPre pre{0.0, 0.0, 0.0};
     if (valid) {
         const int ka   = A.ia[row];
         const int kb   = A.ia[row + 1];
         const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
+        if (lane == 0) pre = epi_prefetch<MODE>(A, a, row, false);   // in flight beside the row pointers
         // U predicated loads per lane are issued together (indices, values, then gathers):
         // a plain unrolled loop would fall into its serial remainder for short trip counts
         constexpr int U = 4;
@@ -408,7 +449,7 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, double* 
     const bool want_dot = a.red.dot_out != nullptr;
     const bool want_n2  = a.red.nrm2_out != nullptr;
     if (valid && lane == 0) {
-        const double out = row_epilogue<MODE>(A, a, row, part, false);
+        const double out = row_epilogue<MODE>(A, a, row, part, false, pre);
         if (want_dot) red_dot = out * a.red.dot_with[row];
         if (want_n2) red_n2 = out * out;
     }
@@ -445,10 +486,12 @@ csr_wide_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, double* pa
     const int*    __restrict__ ja  = A.ja;
     const double* __restrict__ val = A.val;
     double part = 0.0;
+    EpiPre pre{0.0, 0.0, 0.0};
     if (valid) {
         const int ka   = A.ia[row];
         const int kb   = A.ia[row + 1];
         const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
+        if (wl == 0 && lane == 0) pre = epi_prefetch<MODE>(A, a, row, false);
         constexpr int U = 4, STRIDE = 32 * WPR;
         for (int kk = ka + wl * 32 + lane; kk < kb; kk += U * STRIDE) {
             int    col[U];
@@ -483,7 +526,7 @@ csr_wide_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, double* pa
         double acc = s_part[rl * WPR];
 #pragma unroll
         for (int w = 1; w < WPR; ++w) acc += s_part[rl * WPR + w];
-        const double out = row_epilogue<MODE>(A, a, row, acc, false);
+        const double out = row_epilogue<MODE>(A, a, row, acc, false, pre);
         if (want_dot) red_dot = out * a.red.dot_with[row];
         if (want_n2) red_n2 = out * out;
     }
@@ -525,7 +568,7 @@ static void launch_vector(const DevCSR& A, const CsrView& v, const CsrArgs& a, c
 }
 
 // persistent grid: as many CTAs per SM as the stage rings allow
-template <int MODE, bool PATTERN, int T, int UG = 8>
+template <int MODE, bool PATTERN, int T, int UG = 8, bool TP = false>
 static void launch_pipe(const DevCSR& A, const CsrView& v, const CsrArgs& a, const UnitRange& ur, double* part,
                         unsigned int* tick)
 {
@@ -537,7 +580,7 @@ static void launch_pipe(const DevCSR& A, const CsrView& v, const CsrArgs& a, con
     const size_t smem = stage * nst;
     static bool  attr_set = false;
     if (!attr_set) {
-        FC_CUDA(cudaFuncSetAttribute(csr_pipe_kernel<MODE, PATTERN, T, UG>,
+        FC_CUDA(cudaFuncSetAttribute(csr_pipe_kernel<MODE, PATTERN, T, UG, TP>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
@@ -551,7 +594,7 @@ static void launch_pipe(const DevCSR& A, const CsrView& v, const CsrArgs& a, con
     if (c.launch_stream == c.side && c.side != nullptr && per_sm > 2) per_sm -= 1;
     long long grid = (long long)c.sm_count * per_sm;
     if (grid > ur.count) grid = ur.count;
-    FC_LAUNCH((csr_pipe_kernel<MODE, PATTERN, T, UG>), (int)grid, T, smem, v, a, ur, nst,
+    FC_LAUNCH((csr_pipe_kernel<MODE, PATTERN, T, UG, TP>), (int)grid, T, smem, v, a, ur, nst,
               c.opt.strict, part, tick);
 }
 
@@ -592,10 +635,15 @@ static void launch_pattern(const DevCSR& A, const CsrView& v, const CsrArgs& a, 
             // for the 19-entry rows of the first coarse level instead of three) at 64 registers, still
             // 8 CTAs per SM; measured +4 % (level 0) and +10 % (level 1) over the 8-deep variant, which
             // the short rows of the transfer operators keep
-            if (c.opt.gather16_min_avg > 0 && A.rows > 0 && (double)A.nnz >= (double)c.opt.gather16_min_avg * A.rows)
-                launch_pipe<MODE, PATTERN, 128, 16>(A, v, a, ur, part, tick);
-            else
-                launch_pipe<MODE, PATTERN, 128>(A, v, a, ur, part, tick);
+            // two-phase gather rounds per mode (bit MODE of the option): measured on the 7-pt 256^3 hierarchy,
+            // profiles/r02_l1_sweep_scheduling.txt
+            if (c.opt.gather16_min_avg > 0 && A.rows > 0 && (double)A.nnz >= (double)c.opt.gather16_min_avg * A.rows) {
+                if ((c.opt.two_phase_mask >> MODE) & 1) launch_pipe<MODE, PATTERN, 128, 16, true>(A, v, a, ur, part, tick);
+                else launch_pipe<MODE, PATTERN, 128, 16, false>(A, v, a, ur, part, tick);
+            } else {
+                if ((c.opt.two_phase_mask >> MODE) & 1) launch_pipe<MODE, PATTERN, 128, 8, true>(A, v, a, ur, part, tick);
+                else launch_pipe<MODE, PATTERN, 128, 8, false>(A, v, a, ur, part, tick);
+            }
             return;
         default: launch_pipe<MODE, PATTERN, 256>(A, v, a, ur, part, tick); return;
     }
