@@ -57,6 +57,7 @@ bsr_pipe_kernel(const BsrView A, const BsrArgs a, const int nblk, const int nsta
     auto st_ja  = [&](int s) { return reinterpret_cast<int*>(st_val(s) + val_doubles); };
     auto st_ia  = [&](int s) { return st_ja(s) + cap + 8; };
     const double* __restrict__ x = a.x;
+    const int zero = (int)gridDim.y - 1;   // 0 at run time, opaque to the compiler (gather rounds)
 
     auto issue = [&](int blk, int s) {
         const int2 d0 = A.blkdesc[blk], d1 = A.blkdesc[blk + 1];
@@ -138,11 +139,20 @@ bsr_pipe_kernel(const BsrView A, const BsrArgs a, const int nblk, const int nsta
                 double xv[U][NB];
 #pragma unroll
                 for (int u = 0; u < U; ++u) col[u] = (kk + u < kb) ? jbase[kk + u] : -1;
+                // Two phases (all column indices out of shared memory, then all gathers), enforced by a term that is
+                // zero at run time but depends on every index of the round: ptxas otherwise interleaves the LDS and
+                // LDG and can serialise the gathers on a shared scoreboard (spmv.cu, profiles/r02_l1_sweep_scheduling.txt).
+                // 272^3 3x3 blocks, 64 block rows x 8 blocks in flight: Jacobi sweep 3.06 -> 2.25 ms, y = A x 2.79 -> 2.62,
+                // r = b - A x 2.33 -> 2.32 (profiles/r02_bsr272_kernel_shapes.txt)
+                int any = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) any |= col[u];
+                const int dep = any & zero;
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
                     for (int j = 0; j < NB; ++j)
-                        xv[u][j] = (col[u] >= 0) ? __ldg(x + (size_t)col[u] * NB + j) : 0.0;
+                        xv[u][j] = (col[u] >= 0) ? __ldg(x + (size_t)(col[u] + dep) * NB + j) : 0.0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (col[u] < 0) continue;

@@ -45,6 +45,15 @@ def main():
     n = args.n
     zoff = MG.plane_partition(n, world)
     off = [z * n * n for z in zoff]
+    # host memory: the slab setup peaks at about 60 bytes per local nonzero (slab, its diagonal block, FASP's strength
+    # matrix, the embedded Galerkin operands); refuse to start rather than drive the box out of memory
+    import psutil
+    nnz_est = float(args.stencil) * (zoff[rank + 1] - zoff[rank]) * n * n
+    need_all = 60.0 * nnz_est * world
+    avail = psutil.virtual_memory().available
+    log("[config3] host memory: about %.0f GB needed by %d ranks, %.0f GB available" % (need_all / 1e9, world, avail / 1e9))
+    if need_all > 0.9 * avail:
+        raise SystemExit("not enough host memory for the slab setup: need ~%.0f GB, have %.0f GB" % (need_all / 1e9, avail / 1e9))
     t = time.time()
     gen = PB.poisson27 if args.stencil == 27 else PB.poisson7
     A = gen(n, zrange=(zoff[rank], zoff[rank + 1]))
