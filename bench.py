@@ -319,8 +319,15 @@ def run_extras(args, local):
     lock = tempfile.NamedTemporaryFile(prefix="fasp_bench_gpu_", suffix=".lock", delete=False).name
     env = dict(os.environ, LOCAL_RANK=str(local))
     jobs = {}
-    for key, cfg, n, budget in (("config4", 4, args.c4_n, 420), ("config5", 5, args.c5_n, 420)):
-        cmd = [sys.executable, script, "--config", str(cfg), "--n", str(n), "--lock", lock]
+    for key, cfg, n, budget in (("config4", 4, args.c4_n, 420), ("config5", 5, args.c5_n, 420),
+                                ("config3_proxy", 3, args.c3_n, 480)):
+        if cfg == 3:   # configs[2] at the size one dCSRmat (and the sequential oracle) can hold: 27-pt 256^3
+            if n <= 0:
+                continue
+            cmd = [sys.executable, str(ROOT / "scripts" / "bench_config3.py"), "--size", str(n), "--steps", "5",
+                   "--warmup", "3", "--lock", lock]
+        else:
+            cmd = [sys.executable, script, "--config", str(cfg), "--n", str(n), "--lock", lock]
         for kv in args.opt:
             cmd += ["--opt", kv]
         jobs[key] = (subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True),
@@ -440,6 +447,8 @@ def main():
                     help="N = 1: also measure BASELINE configs 4 and 5 (separate processes, bounded) -> extra.config4/5")
     ap.add_argument("--c4-n", type=int, default=256)
     ap.add_argument("--c5-n", type=int, default=272)
+    ap.add_argument("--c3-n", type=int, default=int(os.environ.get("FASP_BENCH_C3N", "256")),
+                    help="extra.config3_proxy: 27-point n^3 through the slab path at every N (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU sample (profiling runs)")
     ap.add_argument("--opt", action="append", default=[], help="libfasp_cuda option key=value")
     ap.add_argument("--agg-rows", type=int, default=8000,

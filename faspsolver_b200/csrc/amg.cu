@@ -56,6 +56,17 @@ void amg_level_vectors(Amg& h, Level& L)
     h.bytes += 4 * sizeof(double) * c;
 }
 
+// work vectors of the polynomial smoother: as long as the level's other vectors (multi-GPU: L.cap must already be
+// the capacity agreed by all ranks, the peers push ghost entries behind the owned part)
+void amg_level_poly_vectors(Amg& h, Level& L)
+{
+    for (int i = 0; i < 3; ++i)
+        if (!L.pv[i]) {
+            L.pv[i] = dalloc<double>((size_t)(L.cap > L.n ? L.cap : L.n) + 8);
+            h.bytes += sizeof(double) * (size_t)(L.cap > L.n ? L.cap : L.n);
+        }
+}
+
 void amg_level_smoother_data(Amg& h, Level& L, const dCSRmat* hostA)
 {
     switch (h.smoother) {
@@ -92,11 +103,7 @@ void amg_level_smoother_data(Amg& h, Level& L, const dCSRmat* hostA)
             L.pk[3] = mu0 * mu1;
             L.pk[4] = 2.0 * L.pk[3] / L.pk[2];
             L.pk[5] = (mu1 - 2.0 * smu0 * smu1 + mu0) / (mu1 + 2.0 * smu0 * smu1 + mu0);
-            for (int i = 0; i < 3; ++i)
-                if (!L.pv[i]) {
-                    L.pv[i] = dalloc<double>((size_t)(L.cap > L.n ? L.cap : L.n) + 8);
-                    h.bytes += sizeof(double) * (size_t)(L.cap > L.n ? L.cap : L.n);
-                }
+            amg_level_poly_vectors(h, L);
             break;
         }
         default: break;

@@ -87,6 +87,7 @@ void amg_setup_coarse(Amg& h);   // dense inverse of the coarsest level, or the 
 void amg_free(Amg* h);
 void amg_set_params(Amg& h, const AMG_param* param);
 void amg_level_smoother_data(Amg& h, Level& L, const dCSRmat* hostA);
+void amg_level_poly_vectors(Amg& h, Level& L);
 void amg_level_vectors(Amg& h, Level& L);
 
 // One preconditioner application z = B r: x0 = 0, h.maxit cycles (PreCSR.c:416-435 +

@@ -70,6 +70,7 @@ struct Options {
     int    gather16_min_avg = 6;   // pipelined kernel: rows averaging >= this use the 16-deep gather variant (0 = never)
     int    rowwise_max      = 64;  // blocks averaging <= this many nonzeros per row: one thread per row
     int    vec_lpr          = 0;   // > 0: force this many lanes per row in the vector kernel
+    int    vec_u            = 4;   // vector kernel: loads in flight per lane (4 / 8; 0 = 8 when a lane owns >= 8 entries)
     int    gs_multicolor    = 0;   // accept SMOOTHER_GS in the cycle as multicolour GS (OpenMP-FASP semantics)
     int    profile          = 0;   // record CUDA events around every matrix kernel (no graphs)
     int    ghost_redundant  = 1;   // multi-GPU: P and R also compute the ghost rows of the level they write to, so the

@@ -261,8 +261,14 @@ static void finish_level(Amg& h, Level& L, int l, int lrep, bool redundant)
         FC_CUDA(cudaMemcpyAsync(&c, dc, 8, cudaMemcpyDeviceToHost, ctx().stream));
         FC_CUDA(cudaStreamSynchronize(ctx().stream));
         dfree(dc);
+        if ((int)c > L.cap && h.smoother == SMOOTHER_POLY)
+            for (int i = 0; i < 3; ++i) {   // allocated with this rank's own ghost count: too short for the peers' pushes
+                dfree(L.pv[i]);
+                L.pv[i] = nullptr;
+            }
         L.cap = (int)c;
         if (l == 0) L.A.vec_cap = L.cap;
+        if (h.smoother == SMOOTHER_POLY && l < nl - 1) amg_level_poly_vectors(h, L);
     }
     amg_level_vectors(h, L);
     if (l <= lrep) {   // partitioned levels + the first replicated one (all-gather target)

@@ -397,7 +397,7 @@ csr_pipe_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, const int 
 // classical-AMG hierarchy (19 ... 1400 nonzeros per row). Lanes of a group read consecutive
 // entries (coalesced), partial sums are combined with warp shuffles.
 // ------------------------------------------------------------------------------------
-template <int MODE, bool PATTERN, int LPR>
+template <int MODE, bool PATTERN, int LPR, int U>
 __global__ void __launch_bounds__(TPB)
 csr_vector_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, double* partials,
                   unsigned int* ticket)
@@ -419,8 +419,8 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, double* 
         const int skip = ModeTraits<MODE>::skipdiag ? ka + A.dpos[row] : -1;
         if (lane == 0) pre = epi_prefetch<MODE>(A, a, row, false);   // in flight beside the row pointers
         // U predicated loads per lane are issued together (indices, values, then gathers):
-        // a plain unrolled loop would fall into its serial remainder for short trip counts
-        constexpr int U = 4;
+        // a plain unrolled loop would fall into its serial remainder for short trip counts.
+        // U = 4, or 8 when a lane owns at least 8 entries of an average row (option vec_u)
         for (int kk = ka + lane; kk < kb; kk += U * LPR) {
             int    col[U];
             double v[U], xv[U];
@@ -553,8 +553,22 @@ static void launch_wide(const DevCSR& A, const CsrView& v, const CsrArgs& a, con
     FC_LAUNCH((csr_wide_kernel<MODE, PATTERN, WPR>), grid, TPB, 0, v, a, ur, part, tick);
 }
 
+template <int MODE, bool PATTERN, int LPR, int U>
+static void launch_vector_u(const DevCSR& A, const CsrView& v, const CsrArgs& a, const UnitRange& ur);
+
 template <int MODE, bool PATTERN, int LPR>
 static void launch_vector(const DevCSR& A, const CsrView& v, const CsrArgs& a, const UnitRange& ur)
+{
+    const Ctx& c = ctx();
+    // 8 loads in flight per lane when the lanes own >= 8 entries of an average row (values only: the pattern-only
+    // transfer operators of UA-AMG have 1-2 entries per row)
+    const bool deep = !PATTERN && (c.opt.vec_u == 8 || (c.opt.vec_u == 0 && A.rows > 0 && (double)A.nnz >= 8.0 * LPR * A.rows));
+    if (deep) launch_vector_u<MODE, PATTERN, LPR, PATTERN ? 4 : 8>(A, v, a, ur);
+    else launch_vector_u<MODE, PATTERN, LPR, 4>(A, v, a, ur);
+}
+
+template <int MODE, bool PATTERN, int LPR, int U>
+static void launch_vector_u(const DevCSR& A, const CsrView& v, const CsrArgs& a, const UnitRange& ur)
 {
     const long long threads = (long long)ur.count * LPR;
     const int       grid    = (int)((threads + TPB - 1) / TPB);
@@ -564,7 +578,7 @@ static void launch_vector(const DevCSR& A, const CsrView& v, const CsrArgs& a, c
         part = red_partials((size_t)grid);
         tick = red_ticket();
     }
-    FC_LAUNCH((csr_vector_kernel<MODE, PATTERN, LPR>), grid, TPB, 0, v, a, ur, part, tick);
+    FC_LAUNCH((csr_vector_kernel<MODE, PATTERN, LPR, U>), grid, TPB, 0, v, a, ur, part, tick);
 }
 
 // persistent grid: as many CTAs per SM as the stage rings allow

@@ -35,7 +35,10 @@ def init_comm(backend=None):
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
-        dist.init_process_group(backend=backend or "gloo", rank=rank, world_size=world)
+        import datetime
+        # a rank that fails must not leave its peers waiting for the default 30 minutes
+        dist.init_process_group(backend=backend or "gloo", rank=rank, world_size=world,
+                                timeout=datetime.timedelta(minutes=10))
     ident = (C.c_ubyte * 128)()
     if rank == 0:
         api.check(L.fasp_cuda_comm_unique_id(ident))
@@ -331,6 +334,20 @@ def bench_main(args):
     api.unpin_host(x_buf)
     solver.close()
     shared.close()
+    # configs[2] proxy (27-point 256^3, the size the sequential oracle can hold) through the slab path, on the same
+    # communicator: the strong-scaling line of the 27-point operator in every scaling run
+    if getattr(args, "extras", 0) and getattr(args, "c3_n", 0) > 0:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+        try:
+            import bench_config3 as C3
+            a3 = C3.parse(["--size", str(args.c3_n), "--steps", "5", "--warmup", "3"] +
+                          [x for kv in getattr(args, "opt", []) for x in ("--opt", kv)])
+            res3 = C3.run(a3, own_comm=False)
+            if out is not None:
+                out["extra"] = {"config3_proxy": res3}
+        except BaseException as e:   # the headline line is never at risk
+            if out is not None:
+                out["extra"] = {"config3_proxy": {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:300])}}
     L.fasp_cuda_comm_finalize()
     return out
 

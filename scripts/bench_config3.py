@@ -5,7 +5,7 @@ built slab by slab with FASP's own per-level routines (faspsolver_b200/slabsetup
 fasp_cuda_krylov_amg_solve on the slab solver. Launch with torchrun (one rank per GPU); N = 1 runs the ordinary
 one-GPU path on the same (one-slab = FASP's own) hierarchy when the matrix fits one dCSRmat.
 
-    python -m torch.distributed.run --nproc-per-node 8 ... scripts/bench_config3.py --n 512
+    python -m torch.distributed.run --nproc-per-node 8 ... scripts/bench_config3.py --size 512
 Prints one JSON line on rank 0."""
 from __future__ import annotations
 
@@ -25,17 +25,26 @@ from faspsolver_b200 import api, fasp_types as T, multigpu as MG, problems as PB
 import bench as B  # noqa: E402
 
 
-def main():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--size", dest="n", type=int, default=512)  # not --n: torchrun's argparse calls it ambiguous
     ap.add_argument("--stencil", type=int, default=27)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--agg-rows", type=int, default=8000)
     ap.add_argument("--opt", action="append", default=[])
     ap.add_argument("--profile", type=int, default=1)
-    args = ap.parse_args()
-    rank, world, local = MG.init_comm()
+    ap.add_argument("--lock", default="", help="one GPU shared with other bench processes: lock file around the GPU phase")
+    return ap.parse_args(argv)
+
+
+def run(args, own_comm=True):
+    """Returns the result dict on rank 0 (None elsewhere). own_comm=False: called inside a process whose
+    communicator is already up (bench.py --gpus N) and stays up."""
+    if own_comm:
+        rank, world, local = MG.init_comm()
+    else:
+        rank, world, local = MG.dist_env()
     L = api.lib()
     for kv in args.opt:
         k, v = kv.split("=")
@@ -68,6 +77,11 @@ def main():
     t = time.time()
     sh = SS.SlabHierarchy(hf, A, off, amg, comm, agg_rows=args.agg_rows, log=log)
     t_setup = time.time() - t
+    lock_f = None
+    if args.lock:
+        import fcntl
+        lock_f = open(args.lock, "w")
+        fcntl.flock(lock_f, fcntl.LOCK_EX)
     t = time.time()
     if world > 1:
         solver = MG.SlabSolver(sh)
@@ -149,6 +163,7 @@ def main():
                     "frac_of_nominal_8000": top["GBps"] / 8000.0, "peak_source": src,
                     "matrix_kernel_ms": sum(x[3] for x in mat), "comm_ms_profiled": sum(x[3] for x in comm_recs),
                     "comm_ops": len(comm_recs)}
+    out = None
     if rank == 0:
         ms = float(np.mean(dev_ms))
         out = {"metric": "amg_pcg_solve_time_poisson3d_%dpt" % args.stencil, "value": ms, "unit": "ms", "n_gpus": world,
@@ -165,17 +180,27 @@ def main():
                "e2e": {"value": float(np.mean(e2e_ms)), "unit": "ms", "h2d_bytes_per_step": int(16 * nloc),
                        "d2h_bytes_per_step": int(8 * nloc)},
                "roofline": roofline, "levels": levels}
-        print(json.dumps(out), flush=True)
-        if not true_rel <= 1e-8 * 1.001:
-            raise RuntimeError("solution misses the tolerance: %g" % true_rel)
+        if not true_rel <= 1e-8 * 1.001:   # reported, not raised: the other ranks are waiting at the barrier below
+            out["error"] = "solution misses the tolerance: true relres %g" % true_rel
     MG.barrier()
     api.unpin_host(b_loc)
     api.unpin_host(x_buf)
     solver.close()
+    if world == 1:
+        hf.amg_free(mgl, amg_g)
     sh.close()
-    if world > 1:
+    if lock_f is not None:
+        import fcntl
+        fcntl.flock(lock_f, fcntl.LOCK_UN)
+        lock_f.close()
+    if world > 1 and own_comm:
         L.fasp_cuda_comm_finalize()
+    return out
 
 
 if __name__ == "__main__":
-    main()
+    res = run(parse())
+    if res is not None:
+        print(json.dumps(res), flush=True)
+        if "error" in res:
+            sys.exit(1)

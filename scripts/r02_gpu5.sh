@@ -24,7 +24,7 @@ echo "== bench"; date
 timeout 600 $TR --master-port 29542 bench.py --gpus $N --steps 10 --warmup 3 > $O/bench.json 2> $O/bench.log; echo "rc=$?"
 tail -c 1800 $O/bench.json; grep "\[bench\]" $O/bench.log | tail
 echo "== config3 slab path n=$C3N"; date
-timeout ${C3T:-900} $TR --master-port 29543 scripts/bench_config3.py --n $C3N --steps 5 --warmup 3 > $O/config3_$C3N.json 2> $O/config3_$C3N.log; echo "rc=$?"
+timeout ${C3T:-900} $TR --master-port 29543 scripts/bench_config3.py --size $C3N --steps 5 --warmup 3 > $O/config3_$C3N.json 2> $O/config3_$C3N.log; echo "rc=$?"
 cut -c1-2500 $O/config3_$C3N.json; grep "config3\|slab setup\|Error\|error" $O/config3_$C3N.log | tail -25
 free -g | head -2
 date

@@ -52,12 +52,10 @@ for smoother, solver_type in ((T.SMOOTHER_L1DIAG, T.SOLVER_CG), (T.SMOOTHER_JACO
         s2.close()
         for k, v in opts:
             api.check(L.fasp_cuda_set_option(k.encode(), 1.0))
-        if opts == (("ghost_redundant", 0.0),):
-            # redundantly computed ghost rows carry the owners' bits: nothing may change
-            assert st2 == st and np.array_equal(x2, x_loc), (rank, opts, st, st2, np.abs(x2 - x_loc).max())
-        else:
-            # without the interior / boundary split the fused dot products are summed in one piece instead of two
-            assert st2 == st and np.abs(x2 - x_loc).max() <= 1e-10 * np.abs(x_loc).max(), (rank, opts, st, st2)
+        # Same iterates up to rounding: the appended ghost rows change the row blocks of P / R (a row near a block
+        # boundary may be summed by a lane group instead of one thread), and without the interior / boundary split
+        # the fused dot products are summed in one piece instead of two
+        assert st2 == st and np.abs(x2 - x_loc).max() <= 1e-10 * np.abs(x_loc).max(), (rank, opts, st, st2)
     parts = [None] * world
     dist.all_gather_object(parts, (s.row0, x_loc))
     s.close()
@@ -113,7 +111,8 @@ for name, gen, n, smoother in (("p27", PB.poisson27, 24, T.SMOOTHER_L1DIAG), ("p
         s.close()
         res[redundant] = (st, x_loc)
     api.check(L.fasp_cuda_set_option(b"ghost_redundant", 1.0))
-    assert res[1.0][0] == res[0.0][0] and np.array_equal(res[1.0][1], res[0.0][1])   # redundant rows carry the owners' bits
+    # redundant ghost rows: the same iterates up to rounding (the row blocks of P / R differ)
+    assert res[1.0][0] == res[0.0][0] and np.abs(res[1.0][1] - res[0.0][1]).max() <= 1e-10 * np.abs(res[0.0][1]).max()
     st, x_loc = res[1.0]
     parts = [None] * world
     dist.all_gather_object(parts, (off[rank], x_loc))
