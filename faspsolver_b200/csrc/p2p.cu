@@ -160,6 +160,11 @@ void p2p_register(void* base, size_t bytes)
     Region R{static_cast<char*>(base), bytes, {nullptr}};
     if (!map_region(R)) fail(ERROR_SOLVER_MISC, "CUDA IPC mapping of a solver buffer failed");
     s.regions.push_back(R);
+    // "the vector exchanged last" is compared by LOCAL address; across solver lifetimes the allocator may hand the
+    // address of a freed vector to a new one on one rank and not on another, and the ranks would then disagree on
+    // the extra barrier (epochs out of step: bench line followed by the slab solver, r02g). Registration is
+    // collective, so forgetting the vector here keeps the ranks' decisions identical.
+    s.last_exchanged = nullptr;
 }
 
 void p2p_unregister(void* base)
@@ -172,6 +177,7 @@ void p2p_unregister(void* base)
             for (int q = 0; q < s.size; ++q)
                 if (q != s.rank && s.regions[i].peer[q]) cudaIpcCloseMemHandle(s.regions[i].peer[q]);
             s.regions.erase(s.regions.begin() + i);
+            s.last_exchanged = nullptr;
             return;
         }
 }
