@@ -19,7 +19,7 @@ cut -c1-3000 $O/config3_$C3N.json; grep "config3\|slab setup\|Error\|error\|memo
 free -g | head -2
 if [ "${WITH_BENCH:-0}" = "1" ]; then
   echo "== bench 7-pt 256^3"; date
-  timeout 600 $TR --master-port 29542 bench.py --gpus $N --steps 10 --warmup 3 > $O/bench.json 2> $O/bench.log; echo "rc=$?"
+  timeout ${BENCHT:-600} $TR --master-port 29542 bench.py --gpus $N --steps 10 --warmup 3 > $O/bench.json 2> $O/bench.log; echo "rc=$?"
   cut -c1-400 $O/bench.json; grep "\[bench\]" $O/bench.log | tail -5
 fi
 date
