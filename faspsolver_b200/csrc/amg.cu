@@ -227,8 +227,12 @@ struct CycleState {
     // multi-GPU, redundant ghost rows: the ghost entries (in A_l's ghost layout) of the level's right-hand side /
     // of the current iterate buffer are up to date, so the next gather of that vector needs no exchange
     std::vector<bool>    bfresh, xfresh;
+    // the restriction that produced this level's right-hand side already wrote the zero-guess sweep x = s b / d
+    // into other(l) (CsrArgs::div_out): the first pre-smoothing sweep only does its bookkeeping
+    std::vector<bool>    prefused;
     CycleState(Amg& h_, const int* d)
-        : h(h_), done(d), cur(h_.nl), xzero(h_.nl, false), bfresh(h_.nl, false), xfresh(h_.nl, false)
+        : h(h_), done(d), cur(h_.nl), xzero(h_.nl, false), bfresh(h_.nl, false), xfresh(h_.nl, false),
+          prefused(h_.nl, false)
     {
     }
     const double* rhs(int l) const { return l == 0 ? b0 : h.lv[l].b; }
@@ -259,9 +263,11 @@ void smooth(CycleState& s, int l, int nsweeps, bool last)
                     // with the ghost rows of b at hand (R computed them) the sweep covers them as well: the
                     // residual that follows then needs no exchange of x
                     const bool ext = s.bfresh[l] && L.dscale_ext != nullptr && !red.dot_out && !red.nrm2_out;
-                    vec_scale_div(out, jac ? h.relax : 1.0, b, ext ? L.dscale_ext : (jac ? L.A.diag : L.A.l1),
-                                  ext ? n + (size_t)L.A.nghost : n, red, s.done);
-                    s.xfresh[l] = ext;
+                    if (!s.prefused[l])
+                        vec_scale_div(out, jac ? h.relax : 1.0, b, ext ? L.dscale_ext : (jac ? L.A.diag : L.A.l1),
+                                      ext ? n + (size_t)L.A.nghost : n, red, s.done);
+                    s.prefused[l] = false;
+                    s.xfresh[l]   = ext;
                 } else {
                     if (s.xzero[l]) {
                         vec_set(s.cur[l], 0.0, n, s.done);
@@ -415,6 +421,25 @@ void run_cycle(CycleState& s)
             r.done = s.done;
             const bool gather_next = L.dist && !h.lv[l + 1].dist;   // agglomeration boundary
             if (gather_next) r.y += L.gdispls[comm_rank()];
+            // Fuse the next level's zero-guess pre-smoothing sweep x = s b / d (a pass over b_{l+1} of its own) into
+            // this kernel's epilogue: same operations on the same values, one launch and 8 B/row less per level.
+            // Not across the agglomeration boundary (every rank needs the whole replicated vector).
+            Level&     Ln   = h.lv[l + 1];
+            const bool jl1  = (h.smoother == SMOOTHER_JACOBI || h.smoother == SMOOTHER_L1DIAG);
+            bool       fuse = ctx().opt.fuse_restrict && jl1 && ctx().opt.zero_guess && h.presmooth >= 1 && l + 1 < nl - 1 &&
+                        !gather_next;
+            if (fuse) {
+                const bool jac  = (h.smoother == SMOOTHER_JACOBI);
+                const bool extn = L.r_ext && Ln.dscale_ext != nullptr;   // R also computes the ghost rows of b_{l+1}
+                if (L.r_ext && !extn) fuse = false;                      // extra rows without a divisor for them
+                if (fuse) {
+                    r.div_out = Ln.xb;   // = other(l+1) once cur[l+1] = xa (below)
+                    r.div_d   = extn ? Ln.dscale_ext : (jac ? Ln.A.diag : Ln.A.l1);
+                    r.div_s   = jac ? h.relax : 1.0;
+                    if (!r.div_d) fuse = false, r.div_out = nullptr;
+                    else r.mode = CSR_MXV_DIV;
+                }
+            }
             csr_launch(L.R, r);
             if (gather_next)
                 comm_allgatherv(r.y, L.gcounts[comm_rank()], h.lv[l + 1].b, L.gcounts, L.gdispls, s.done);
@@ -423,6 +448,7 @@ void run_cycle(CycleState& s)
             s.xzero[l]  = true;   // fasp_dvec_set(..., 0.0) (:151) is folded into the next writer
             s.xfresh[l] = false;
             s.bfresh[l] = h.lv[l - 1].r_ext;   // R also produced the ghost rows of this level's right-hand side
+            s.prefused[l] = fuse;
         }
 
         coarse_solve(s, false);

@@ -170,6 +170,7 @@ static int* option_slot(const char* key)
     if (!strcmp(key, "wide_threads")) return &o.wide_threads;
     if (!strcmp(key, "vec_lpr")) return &o.vec_lpr;
     if (!strcmp(key, "vec_u")) return &o.vec_u;
+    if (!strcmp(key, "fuse_restrict")) return &o.fuse_restrict;
     if (!strcmp(key, "gs_multicolor")) return &o.gs_multicolor;
     if (!strcmp(key, "ghost_redundant")) return &o.ghost_redundant;
     if (!strcmp(key, "overlap")) return &o.overlap;

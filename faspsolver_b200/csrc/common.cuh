@@ -70,13 +70,16 @@ struct Options {
     int    gather16_min_avg = 6;   // pipelined kernel: rows averaging >= this use the 16-deep gather variant (0 = never)
     int    rowwise_max      = 64;  // blocks averaging <= this many nonzeros per row: one thread per row
     int    vec_lpr          = 0;   // > 0: force this many lanes per row in the vector kernel
+    int    fuse_restrict    = 1;   // R's epilogue also writes the next level's zero-guess sweep x = s b / d
     int    vec_u            = 4;   // vector kernel: loads in flight per lane (4 / 8; 0 = 8 when a lane owns >= 8 entries)
     int    gs_multicolor    = 0;   // accept SMOOTHER_GS in the cycle as multicolour GS (OpenMP-FASP semantics)
     int    profile          = 0;   // record CUDA events around every matrix kernel (no graphs)
     int    ghost_redundant  = 1;   // multi-GPU: P and R also compute the ghost rows of the level they write to, so the
                                    // post-smoother and the residual start without their own ghost exchange (2 per level)
     int    overlap          = 1;   // multi-GPU: rows without ghost columns run on a second stream while the ghosts travel
-    int    overlap_min_rows = 256; // ... when the operator's interior has at least this many rows
+    int    overlap_min_rows = 8192; // ... when the operator's interior has at least this many rows: on smaller slabs the two extra
+                                    // graph nodes cost more than the overlap hides (4 GPUs, 7-pt 256^3: 33.2 ms with 256, 27.1 with
+                                    // 8192, 31.2 with 100000, 32.2 without overlap; profiles/r02_dist_sweep_N4.txt)
     int    bsr_rb           = 64;  // BSR pipelined kernel: block rows per CTA (32 / 64), nb <= 4. Measured on the 3x3-block
                                    // 7-point matrix (160^3): 32/4 0.69 of the copy peak, 32/8 0.76, 64/4 0.78, 64/8 0.81-0.85
     int    bsr_u            = 8;   // its blocks in flight per thread (4 / 8), nb <= 4
@@ -227,7 +230,9 @@ enum CsrMode {
     CSR_L1 = 4,      // y = x + (b - A x)/l1
     CSR_POLY1 = 5,   // poly smoother first step  (see spmv.cu)
     CSR_POLYJ = 6,   // poly smoother recurrence step
-    CSR_RESID_DINV = 7  // y = b - A x ; aux_out = dinv .* y   (poly smoother residual)
+    CSR_RESID_DINV = 7, // y = b - A x ; aux_out = dinv .* y   (poly smoother residual)
+    CSR_MXV_DIV = 8     // y = A x ; div_out = div_s * y ./ div_d  (restriction + the next level's zero-guess sweep).
+                        // A mode of its own so that the code of plain y = A x stays exactly what was measured.
 };
 
 struct CsrArgs {
@@ -242,6 +247,10 @@ struct CsrArgs {
     double*       v0_out = nullptr; // POLY1: v0 out ; POLYJ: new v0 (= old v1)
     double*       u_acc  = nullptr; // POLYJ (last step): u += vnew
     double        k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0;
+    // CSR_MXV_DIV extra output (restriction fused with the next level's zero-guess sweep): div_out_i = div_s * y_i / div_d_i
+    double*       div_out = nullptr;
+    const double* div_d   = nullptr;
+    double        div_s   = 1.0;
     Reduce        red;
     const double* red_add = nullptr;     // totals of the other part of a split launch, added in the finalize step
     bool          skip_halo = false;     // multi-GPU: the ghosts of x are already up to date (computed redundantly)

@@ -78,7 +78,8 @@ template <int MODE>
 __device__ __forceinline__ EpiPre epi_prefetch(const CsrView& A, const CsrArgs& a, int row, bool exact)
 {
     EpiPre e{0.0, 0.0, 0.0};
-    if (MODE == CSR_AXPY) e.p0 = a.y[row];
+    if (MODE == CSR_MXV_DIV) e.p0 = a.div_d[row];
+    else if (MODE == CSR_AXPY) e.p0 = a.y[row];
     else if (MODE == CSR_RESID) e.p0 = a.b[row];
     else if (MODE == CSR_RESID_DINV) e.p0 = a.b[row], e.p1 = A.dinv[row];
     else if (MODE == CSR_JACOBI) e.p0 = exact ? 0.0 : a.b[row], e.p1 = A.diag[row], e.p2 = a.x[row];
@@ -95,6 +96,10 @@ __device__ __forceinline__ double row_epilogue(const CsrView& A, const CsrArgs& 
     double out;
     if (MODE == CSR_MXV) {
         out = acc;
+    } else if (MODE == CSR_MXV_DIV) {
+        out = acc;   // + x_i = s * b_i / d_i of the next level's zero-guess sweep (k_scale_div), same roundings
+        const double num = (a.div_s == 1.0) ? out : __dmul_rn(a.div_s, out);
+        a.div_out[row]   = (fabs(pre.p0) > SMALLREAL) ? __ddiv_rn(num, pre.p0) : 0.0;
     } else if (MODE == CSR_AXPY) {
         // BlaSpmvCSR.c:509-590: alpha == 1 / -1 / general (temp*alpha added last)
         const double y0 = pre.p0;
@@ -681,6 +686,7 @@ static void launch_any(const DevCSR& A, const CsrView& v, const CsrArgs& a, int 
         case CSR_POLY1: launch_mode<CSR_POLY1>(A, v, a, which); break;
         case CSR_POLYJ: launch_mode<CSR_POLYJ>(A, v, a, which); break;
         case CSR_RESID_DINV: launch_mode<CSR_RESID_DINV>(A, v, a, which); break;
+        case CSR_MXV_DIV: launch_mode<CSR_MXV_DIV>(A, v, a, which); break;
         default: fail(ERROR_INPUT_PAR, "csr_launch: unknown mode %d", a.mode);
     }
 }
@@ -694,10 +700,11 @@ void csr_launch(const DevCSR& A, const CsrArgs& a_in)
         return;
     }
     Ctx&       c       = ctx();
-    const bool reads_y = (a_in.mode == CSR_AXPY || a_in.mode == CSR_RESID || a_in.mode >= CSR_JACOBI);
+    const bool reads_y = (a_in.mode == CSR_AXPY || a_in.mode == CSR_RESID ||
+                          (a_in.mode >= CSR_JACOBI && a_in.mode != CSR_MXV_DIV));
     double     pbytes  = csr_spmv_bytes(A, reads_y);
     if (a_in.mode == CSR_JACOBI || a_in.mode == CSR_L1) pbytes += 16.0 * A.rows;   // + u read, d read
-    if (a_in.mode >= CSR_POLY1) pbytes += 16.0 * A.rows;
+    if (a_in.mode >= CSR_POLY1) pbytes += 16.0 * A.rows;   // incl. CSR_MXV_DIV: + d read, x written
     const CsrArgs& a = a_in;
     switch (a.mode) {
         case CSR_JACOBI:

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
+from faspsolver_b200 import api
 from faspsolver_b200 import fasp_types as T
 from faspsolver_b200 import problems as PB
 from faspsolver_b200.fasp_types import CSR
@@ -214,3 +215,44 @@ def test_gs_multicolor_drop_in_matches_oracle(gpu, data):
             vu, vb = T.Vec(u0.copy()), T.Vec(b)
             assert gpu.fasp_cuda_smoother_dcsr_gs_multicolor(vu.ptr(), A.ptr(), vb.ptr(), 2, order) == 0
             assert np.abs(vu.a - want).max() <= 1e-13 * max(1.0, np.abs(want).max()), order
+
+
+def test_kernel_scheduling_options_do_not_change_results(gpu, ref, data):
+    """two_phase_mask (gather rounds in two enforced phases, per mode) and vec_u (loads in flight per lane of the
+    vector kernel) only change instruction scheduling: y = Ax, y += aAx and the smoother sweeps must be bit-identical
+    for every setting, and equal to the reference where the reference order is kept (one thread per row)."""
+    rng = np.random.default_rng(16)
+    mats = [("p7_24", PB.poisson7(24)), ("p27_12", PB.poisson27(12)), ("FE", data["FE"])]
+    # a few long rows -> vector kernel
+    mats.append(("dense_rows", T.CSR.from_scipy(sp.random(400, 3000, density=0.2, format="csr", random_state=3))))
+    settings = [(b"two_phase_mask", 0.0), (b"two_phase_mask", 255.0), (b"two_phase_mask", 6.0), (b"vec_u", 8.0), (b"vec_u", 4.0)]
+    try:
+        for name, A in mats:
+            x = rng.uniform(-1, 1, A.shape[1])
+            y0 = rng.uniform(-1, 1, A.shape[0])
+            outs = []
+            for key, val in settings:
+                api.check(gpu.fasp_cuda_set_option(key, val))
+                y = np.empty(A.shape[0])
+                assert gpu.fasp_cuda_blas_dcsr_mxv(A.ptr(), T.as_preal(x), T.as_preal(y)) == 0
+                z = y0.copy()
+                assert gpu.fasp_cuda_blas_dcsr_aAxpy(-1.0, A.ptr(), T.as_preal(x), T.as_preal(z)) == 0
+                outs.append((y, z))
+            for y, z in outs[1:]:
+                assert np.array_equal(y, outs[0][0]) and np.array_equal(z, outs[0][1]), name
+            if name != "dense_rows":
+                assert np.array_equal(outs[0][0], ref.mxv(A, x)), name
+        # the L1 sweep through the smoother drop-in (square matrices)
+        for name, A in mats[:3]:
+            b = rng.uniform(-1, 1, A.shape[0])
+            res = []
+            for key, val in settings[:3]:
+                api.check(gpu.fasp_cuda_set_option(key, val))
+                u = T.Vec(np.zeros(A.shape[0]))
+                vb = T.Vec(b)
+                assert gpu.fasp_cuda_smoother_dcsr_L1diag(u.ptr(), 0, A.shape[0] - 1, 1, A.ptr(), vb.ptr(), 2) == 0
+                res.append(u.a.copy())
+            assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2]), name
+    finally:
+        gpu.fasp_cuda_set_option(b"two_phase_mask", 6.0)
+        gpu.fasp_cuda_set_option(b"vec_u", 4.0)
