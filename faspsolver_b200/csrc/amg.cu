@@ -426,8 +426,10 @@ void run_cycle(CycleState& s)
             // Not across the agglomeration boundary (every rank needs the whole replicated vector).
             Level&     Ln   = h.lv[l + 1];
             const bool jl1  = (h.smoother == SMOOTHER_JACOBI || h.smoother == SMOOTHER_L1DIAG);
-            bool       fuse = ctx().opt.fuse_restrict && jl1 && ctx().opt.zero_guess && h.presmooth >= 1 && l + 1 < nl - 1 &&
-                        !gather_next;
+            // Default: in the multi-GPU solve only. On one GPU it is a wash (R_0 +32 us, the saved sweep 33 us: 60.9 vs
+            // 59.8 ms per solve); across GPUs the solve is bound by the number of graph nodes and every launch counts.
+            const bool want = ctx().opt.fuse_restrict == 2 || (ctx().opt.fuse_restrict == 1 && h.dist);
+            bool       fuse = want && jl1 && ctx().opt.zero_guess && h.presmooth >= 1 && l + 1 < nl - 1 && !gather_next;
             if (fuse) {
                 const bool jac  = (h.smoother == SMOOTHER_JACOBI);
                 const bool extn = L.r_ext && Ln.dscale_ext != nullptr;   // R also computes the ghost rows of b_{l+1}

@@ -71,7 +71,10 @@ struct Options {
     int    rowwise_max      = 64;  // blocks averaging <= this many nonzeros per row: one thread per row
     int    vec_lpr          = 0;   // > 0: force this many lanes per row in the vector kernel
     int    fuse_restrict    = 1;   // R's epilogue also writes the next level's zero-guess sweep x = s b / d
-    int    vec_u            = 4;   // vector kernel: loads in flight per lane (4 / 8; 0 = 8 when a lane owns >= 8 entries)
+                                   // (1: multi-GPU hierarchies only, 2: always, 0: never)
+    int    vec_u            = 0;   // vector kernel: loads in flight per lane (4 / 8; 0 = 8 when a lane owns >= 12 entries of an
+                                   // average row: levels 4-7 of the 256^3 hierarchy gain 5-13 %, level 3 (8 per lane) loses 4 %,
+                                   // profiles/r02_vector_kernel_depth.txt)
     int    gs_multicolor    = 0;   // accept SMOOTHER_GS in the cycle as multicolour GS (OpenMP-FASP semantics)
     int    profile          = 0;   // record CUDA events around every matrix kernel (no graphs)
     int    ghost_redundant  = 1;   // multi-GPU: P and R also compute the ghost rows of the level they write to, so the

@@ -425,7 +425,7 @@ csr_vector_kernel(const CsrView A, const CsrArgs a, const UnitRange ur, double* 
         if (lane == 0) pre = epi_prefetch<MODE>(A, a, row, false);   // in flight beside the row pointers
         // U predicated loads per lane are issued together (indices, values, then gathers):
         // a plain unrolled loop would fall into its serial remainder for short trip counts.
-        // U = 4, or 8 when a lane owns at least 8 entries of an average row (option vec_u)
+        // U = 4, or 8 when a lane owns at least 12 entries of an average row (option vec_u)
         for (int kk = ka + lane; kk < kb; kk += U * LPR) {
             int    col[U];
             double v[U], xv[U];
@@ -565,9 +565,9 @@ template <int MODE, bool PATTERN, int LPR>
 static void launch_vector(const DevCSR& A, const CsrView& v, const CsrArgs& a, const UnitRange& ur)
 {
     const Ctx& c = ctx();
-    // 8 loads in flight per lane when the lanes own >= 8 entries of an average row (values only: the pattern-only
+    // 8 loads in flight per lane when the lanes own >= 12 entries of an average row (values only: the pattern-only
     // transfer operators of UA-AMG have 1-2 entries per row)
-    const bool deep = !PATTERN && (c.opt.vec_u == 8 || (c.opt.vec_u == 0 && A.rows > 0 && (double)A.nnz >= 8.0 * LPR * A.rows));
+    const bool deep = !PATTERN && (c.opt.vec_u == 8 || (c.opt.vec_u == 0 && A.rows > 0 && (double)A.nnz >= 12.0 * LPR * A.rows));
     if (deep) launch_vector_u<MODE, PATTERN, LPR, PATTERN ? 4 : 8>(A, v, a, ur);
     else launch_vector_u<MODE, PATTERN, LPR, 4>(A, v, a, ur);
 }

@@ -9,19 +9,25 @@ The hierarchy is therefore built slab by slab with FASP's OWN per-level routines
     1. A_loc  = the slab's diagonal block (owned rows x owned columns); the entries that couple to another
                 slab are lumped onto the diagonal, so that rows next to a seam keep their row sum (the
                 interpolation weights of fasp_amg_interp then still add up to one there);
-    2. fasp_amg_coarsening_rs(A_loc) + fasp_amg_interp(A_loc)  -> P_loc (PreAMGCoarsenRS.c:76, PreAMGInterp.c:66);
-       coarse points are numbered rank by rank (coarse offsets = prefix sum of the ranks' counts), so
-       P = blockdiag(P_loc) and R = P^T (fasp_dcsr_trans) stay local;
-    3. Galerkin product with the TRUE slab of A_l (all couplings across the seams): the rows of P that belong
-       to the slab's ghost columns are fetched from their owners, then fasp_blas_dcsr_rap (BlaSpmvCSR.c:999)
-       forms this rank's rows of A_{l+1} = R A_l P in global coarse numbering.
+    2. fasp_amg_coarsening_rs(A_loc) + fasp_amg_interp(A_loc)  -> C/F splitting and P_loc (PreAMGCoarsenRS.c:76,
+       PreAMGInterp.c:66); coarse points are numbered rank by rank (coarse offsets = prefix sum of the ranks' counts);
+    2b. the F rows that couple across a seam are interpolated again from their FULL rows of A_l, with the C/F marks
+       and coarse numbers of the points across the seam fetched from their owners (seam_interpolation: FASP's
+       strength rule, direct-interpolation weights and truncation, restated for these rows only). Slab-local rows
+       are one-sided there and cost the cycle half its convergence rate; R = P^T then has entries from the
+       neighbours' rows (distributed_transpose);
+    3. Galerkin product with the TRUE operator: the rows of A_l and P that the rank's rows of R reach beyond its
+       slab are fetched from their owners, then fasp_blas_dcsr_rap (BlaSpmvCSR.c:999) forms this rank's rows of
+       A_{l+1} = R A_l P in global coarse numbering.
   Below `agg_rows` global rows the level is gathered on every rank and FASP's unmodified fasp_amg_setup_rs
   builds the replicated rest of the hierarchy.
 
 With ONE rank every step degenerates to the reference's own call sequence on the same data, so the hierarchy
-is bit-identical to fasp_amg_setup_rs (tests/test_slab_setup.py). With several ranks the coarsening near the
-seams differs from the global one (slab-local C/F splitting, as in hypre's "RS0"); the hierarchy is still a
-Galerkin hierarchy of the true operator. Its oracle: the slabs are assembled into global CSR matrices (small
+is bit-identical to fasp_amg_setup_rs (tests/test_slab_setup.py). With several ranks the C/F splitting near the
+seams differs from the global one (slab-local, as in hypre's "RS0"); the hierarchy is still a Galerkin hierarchy
+of the true operator. Iterations of the reference's CPU PCG on the assembled hierarchy, 27-point operator:
+48^3 / 64^3 on 4 slabs 11 / 12 (global hierarchy 11; without step 2b: 20 / 23), 96^3 on 2 slabs 12 (12; 24),
+128^3 on 2 slabs 18 (13; 30). Its oracle: the slabs are assembled into global CSR matrices (small
 sizes) and handed to the REFERENCE's fasp_solver_dcsr_pcg + fasp_precond_amg (`assemble_global`).
 
 Host-side plumbing (torch.distributed, gloo) moves index lists and matrix rows between the ranks at setup;
@@ -201,7 +207,7 @@ class _Fasp:
         out = None
         if ok:
             L.fasp_amg_interp(A_loc.ptr(), C.byref(vertices), C.byref(P), C.byref(S), C.byref(param))
-            out = CSR.from_struct(P)
+            out = (CSR.from_struct(P), vert[:n].copy())
         if S.IA:
             L.fasp_mem_free(C.cast(S.IA, C.c_void_p))
         if S.JA:
@@ -223,6 +229,142 @@ class _Fasp:
         out = CSR.from_struct(B)
         self.L.fasp_dcsr_free(C.byref(B))
         return out
+
+
+CGPT, FGPT = 1, 0   # fasp_const.h: coarse / fine point in the C/F marker
+SMALLREAL = 1e-20   # fasp_const.h
+
+
+def fetch_ints(comm: HostComm, x_loc, off, want):
+    """fetch_entries for an integer vector."""
+    return fetch_entries(comm, np.asarray(x_loc, dtype=np.float64), off, want).astype(np.int64)
+
+
+def seam_interpolation(A: CSR, c0, c1, vert, cnum, ghosts, ghost_cnum, amg):
+    """Interpolation rows of the F points that couple across a seam, from their FULL rows of A.
+
+    The slab-local rows FASP computed for them use only the coarse points of their own side — a one-sided formula
+    that costs the cycle half its convergence rate (27-pt 48^3 on 4 slabs: 20 iterations against 11 with the global
+    hierarchy). Here the same formulas FASP applies to every F row are applied to the complete row, the coarse
+    points across the seam included (their C/F marks and coarse numbers come from their owners):
+      strength   a_ij < strong_threshold * min_k a_ik, none if |row sum| > max_row_sum |a_ii|   (PreAMGCoarsenRS.c:300-330)
+      pattern    the strong C neighbours                                                          (form_P_pattern_dir)
+      weights    direct interpolation, negative and positive entries scaled separately            (PreAMGInterp.c:430-478)
+      truncation entries below truncation_threshold * max dropped, the rest rescaled              (PreAMGInterp.c:127-210)
+    cnum[i]: global coarse number of owned point i or -1; ghost_cnum likewise for `ghosts`.
+    Returns (rows, ia, ja, val): new P rows (global coarse columns) for the seam F rows that have a pattern."""
+    n = A.shape[0]
+    out_idx = np.nonzero((A.ja < c0) | (A.ja >= c1))[0]
+    seam = np.unique(np.searchsorted(A.ia, out_idx, side="right") - 1)
+    seam = seam[vert[seam] != CGPT]     # F points and the points FASP found isolated inside the slab (ISPT)
+    if seam.size == 0:
+        return seam, np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0)
+    cnt = (A.ia[seam + 1] - A.ia[seam]).astype(np.int64)
+    e = _ranges(A.ia[seam].astype(np.int64), cnt)             # entries of the seam rows
+    r = np.repeat(np.arange(seam.size), cnt)                    # their row number within `seam`
+    col = A.ja[e].astype(np.int64)
+    a = A.val[e]
+    grow = seam[r] + c0                                          # global row
+    isdiag = col == grow
+    ns = seam.size
+    aii = np.zeros(ns); aii[r[isdiag]] = a[isdiag]
+    row_min = np.minimum.reduceat(a, np.cumsum(cnt) - cnt)     # incl. the diagonal, as the reference (min with 0)
+    row_min = np.minimum(row_min, 0.0)
+    row_sum = np.add.reduceat(a, np.cumsum(cnt) - cnt)
+    all_weak = np.abs(row_sum) > amg.max_row_sum * np.abs(aii)
+    strong = (a < amg.strong_threshold * row_min[r]) & ~all_weak[r] & ~isdiag
+    inside = (col >= c0) & (col < c1)
+    cn = np.full(col.size, -1, dtype=np.int64)
+    cn[inside] = cnum[col[inside] - c0]
+    if (~inside).any():
+        cn[~inside] = ghost_cnum[np.searchsorted(ghosts, col[~inside])]
+    pat = strong & (cn >= 0)
+    off_d = ~isdiag
+    neg, pos = a < 0, a > 0                                      # the reference: "> 0" positive, else negative
+    amN = np.bincount(r[off_d & ~pos], weights=a[off_d & ~pos], minlength=ns)
+    apN = np.bincount(r[off_d & pos], weights=a[off_d & pos], minlength=ns)
+    amP = np.bincount(r[pat & ~pos], weights=a[pat & ~pos], minlength=ns)
+    apP = np.bincount(r[pat & pos], weights=a[pat & pos], minlength=ns)
+    npc = np.bincount(r[pat & pos], minlength=ns)
+    amP = np.where(amP < -SMALLREAL, amP, -SMALLREAL)
+    apP = np.where(apP > SMALLREAL, apP, SMALLREAL)
+    alpha = amN / amP
+    beta = np.where(npc > 0, apN / apP, 0.0)
+    aii_eff = np.where(npc > 0, aii, aii + apN)
+    w = np.where(pos, -beta[r] * a / aii_eff[r], -alpha[r] * a / aii_eff[r])
+    # pattern entries only, then the truncation step
+    pr, pc, pw = r[pat], cn[pat], w[pat]
+    has = np.bincount(pr, minlength=ns) > 0
+    maxpos = np.zeros(ns); np.maximum.at(maxpos, pr[pw > 0], pw[pw > 0])
+    minneg = np.zeros(ns); np.minimum.at(minneg, pr[pw <= 0], pw[pw <= 0])
+    sum_pos = np.bincount(pr[pw > 0], weights=pw[pw > 0], minlength=ns)
+    sum_neg = np.bincount(pr[pw <= 0], weights=pw[pw <= 0], minlength=ns)
+    eps_tr = amg.truncation_threshold
+    keep_pos = pw >= (maxpos * eps_tr)[pr]
+    keep_neg = ~keep_pos & (pw <= (minneg * eps_tr)[pr])
+    tsum_pos = np.bincount(pr[keep_pos], weights=pw[keep_pos], minlength=ns)
+    tsum_neg = np.bincount(pr[keep_neg], weights=pw[keep_neg], minlength=ns)
+    fac_pos = np.where(tsum_pos > SMALLREAL, sum_pos / np.where(tsum_pos > SMALLREAL, tsum_pos, 1.0), 1.0)
+    fac_neg = np.where(tsum_neg < -SMALLREAL, sum_neg / np.where(tsum_neg < -SMALLREAL, tsum_neg, 1.0), 1.0)
+    keep = keep_pos | keep_neg
+    kr, kc = pr[keep], pc[keep]
+    kw = np.where(keep_pos[keep], pw[keep] * fac_pos[kr], pw[keep] * fac_neg[kr])
+    rows_out = np.nonzero(has)[0]
+    cnt_out = np.bincount(kr, minlength=ns)[rows_out]
+    ia = np.zeros(rows_out.size + 1, dtype=np.int64)
+    np.cumsum(cnt_out, out=ia[1:])
+    return seam[rows_out], ia, kc.astype(np.int32), kw      # entries are already grouped by row (ascending)
+
+
+def replace_rows(P: CSR, rows, ia_new, ja_new, val_new):
+    """P with the given rows replaced (rows ascending; ia_new/ja_new/val_new their CSR)."""
+    if len(rows) == 0:
+        return P
+    n = P.shape[0]
+    cnt = np.diff(P.ia).astype(np.int64)
+    cnt[rows] = np.diff(ia_new)
+    ia = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(cnt, out=ia[1:])
+    ja = np.empty(int(ia[-1]), dtype=np.int32)
+    val = np.empty(int(ia[-1]))
+    repl = np.zeros(n, dtype=bool)
+    repl[rows] = True
+    old_rows = np.repeat(np.arange(n), np.diff(P.ia))
+    keep = ~repl[old_rows]
+    dst = _ranges(ia[:-1][~repl], cnt[~repl])
+    ja[dst] = P.ja[keep]
+    val[dst] = P.val[keep]
+    dst2 = _ranges(ia[:-1][rows], np.diff(ia_new).astype(np.int64))
+    ja[dst2] = ja_new
+    val[dst2] = val_new
+    return CSR(n, P.shape[1], ia.astype(np.int32), ja, val)
+
+
+def distributed_transpose(comm: HostComm, P: CSR, off, coff):
+    """R = P^T for a row-partitioned P (global coarse columns): this rank's rows of R are its own coarse points,
+    the entries of P rows that interpolate from another rank's coarse points travel to that rank. Entries of a
+    row of R ascend in the fine index, as fasp_dcsr_trans leaves them."""
+    rank = comm.rank
+    r0, k0, k1 = int(off[rank]), int(coff[rank]), int(coff[rank + 1])
+    rows = np.repeat(np.arange(P.shape[0], dtype=np.int64), np.diff(P.ia)) + r0
+    cols = P.ja.astype(np.int64)
+    owner = np.searchsorted(np.asarray(coff), cols, side="right") - 1
+    send = []
+    for q in range(comm.world):
+        m = owner == q
+        send.append(None if (q == rank or not m.any()) else (rows[m], cols[m], P.val[m]))
+    got = comm.alltoall(send) if comm.world > 1 else [None]
+    mine = owner == rank
+    tr, tc, tv = [rows[mine]], [cols[mine]], [P.val[mine]]
+    for q in range(comm.world):
+        if q != rank and got[q] is not None:
+            tr.append(got[q][0]); tc.append(got[q][1]); tv.append(got[q][2])
+    tr, tc, tv = np.concatenate(tr), np.concatenate(tc) - k0, np.concatenate(tv)
+    order = np.lexsort((tr, tc))
+    tr, tc, tv = tr[order], tc[order], tv[order]
+    ia = np.zeros(k1 - k0 + 1, dtype=np.int64)
+    np.cumsum(np.bincount(tc, minlength=k1 - k0), out=ia[1:])
+    return CSR(k1 - k0, int(off[-1]), ia.astype(np.int32), tr.astype(np.int32), tv)
 
 
 def local_block(A: CSR, c0, c1):
@@ -258,7 +400,8 @@ class SlabLevel:
 
 
 class SlabHierarchy:
-    def __init__(self, hf, A_slab: CSR, off, amg, comm: HostComm | None = None, agg_rows=8000, log=None):
+    def __init__(self, hf, A_slab: CSR, off, amg, comm: HostComm | None = None, agg_rows=8000, log=None,
+                 seam_interp=True):
         self.hf, self.amg = hf, amg
         self.comm = comm or HostComm()
         self.F = _Fasp(hf)
@@ -277,8 +420,8 @@ class SlabHierarchy:
             c0, c1 = int(off[rank]), int(off[rank + 1])
             n_loc = c1 - c0
             assert A.shape[0] == n_loc
-            P_loc = self.F.coarsen_interp(local_block(A, c0, c1), amg) if n_loc > 0 else None
-            info = comm.allgather((P_loc is not None or n_loc == 0, 0 if P_loc is None else P_loc.shape[1]))
+            got = self.F.coarsen_interp(local_block(A, c0, c1), amg) if n_loc > 0 else None
+            info = comm.allgather((got is not None or n_loc == 0, 0 if got is None else got[0].shape[1]))
             if not all(ok for ok, _ in info):
                 break
             ncs = np.array([nc for _, nc in info], dtype=np.int64)
@@ -286,23 +429,39 @@ class SlabHierarchy:
             NC = int(coff[-1])
             if NC >= 2 ** 31 - 1:
                 raise ValueError("coarse level exceeds 32-bit column numbers")
-            if P_loc is None:
-                P_loc = CSR(0, 0, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0))
+            if got is None:
+                P_loc, vert = CSR(0, 0, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0)), np.zeros(0, np.int32)
+            else:
+                P_loc, vert = got
             nc_loc = P_loc.shape[1]
-            R_loc = self.F.trans(P_loc)
             P_glob = CSR(n_loc, NC, P_loc.ia, P_loc.ja + np.int32(coff[rank]), P_loc.val)
             ghosts = ghost_columns(A, c0, c1)
-            P_gh = fetch_rows(comm, P_glob, off, ghosts)
-            A_next = self._galerkin(A, c0, c1, ghosts, P_loc, P_gh, R_loc, int(coff[rank]), NC)
+            n_seam = 0
+            if comm.world > 1 and seam_interp:
+                # C/F marks and coarse numbers of the points across the seams come from their owners; the F rows
+                # that couple across a seam are then interpolated from their full rows (seam_interpolation)
+                cnum = np.full(n_loc, -1, dtype=np.int64)
+                cidx = np.nonzero(vert == CGPT)[0]
+                cnum[cidx] = int(coff[rank]) + np.arange(cidx.size)
+                ghost_cnum = fetch_ints(comm, cnum, off, ghosts)
+                rows, ia_n, ja_n, val_n = seam_interpolation(A, c0, c1, vert, cnum, ghosts, ghost_cnum, amg)
+                P_glob = replace_rows(P_glob, rows, ia_n, ja_n, val_n)
+                n_seam = int(rows.size)
+            if comm.world > 1:
+                R_glob = distributed_transpose(comm, P_glob, off, coff)
+            else:
+                R_loc = self.F.trans(P_loc)
+                R_glob = CSR(nc_loc, int(off[-1]), R_loc.ia, R_loc.ja + np.int32(c0), R_loc.val)
+            A_next, P_gh = self._galerkin(A, off, coff, ghosts, P_glob, R_glob)
             lv = SlabLevel()
             lv.A, lv.off, lv.coff, lv.ghosts = A, off, coff, ghosts
             lv.P = _stack_rows(P_glob, P_gh)
             lv.n_pext = int(ghosts.size)
-            lv.R = CSR(nc_loc, int(off[-1]), R_loc.ia, R_loc.ja + np.int32(c0), R_loc.val)
+            lv.R = R_glob
             lv.n_rext = 0
             self.levels.append(lv)
-            log("[slab setup] level %d: %d rows (%d here, %d ghosts) -> %d coarse rows" %
-                (len(self.levels) - 1, int(off[-1]), n_loc, ghosts.size, NC))
+            log("[slab setup] level %d: %d rows (%d here, %d ghosts, %d seam rows re-interpolated) -> %d coarse rows" %
+                (len(self.levels) - 1, int(off[-1]), n_loc, ghosts.size, n_seam, NC))
             A, off = A_next, coff
         if not self.levels:
             raise ValueError("slab setup: the finest level could not be coarsened on every rank")
@@ -330,35 +489,67 @@ class SlabHierarchy:
         log("[slab setup] replicated from level %d: %d rows, %d more levels" %
             (len(self.levels), N, self.tail[0].num_levels))
 
-    def _galerkin(self, A, c0, c1, ghosts, P_loc, P_gh, R_loc, cbase, NC):
-        """This rank's rows of R A P. fasp_blas_dcsr_rap assumes square operands (its marker arrays are sized by
-        the row counts, BlaSpmvCSR.c:1042-1050), so the slab is embedded: fine space = owned + ghost columns
-        (ghost ROWS empty), coarse space = owned coarse points + the coarse points the ghost rows of P reach."""
-        n_loc, nc_loc, ng = c1 - c0, P_loc.shape[1], int(ghosts.size)
-        if ng == 0:
-            return_cols = None
+    def _galerkin(self, A, off, coff, ghosts, P, R):
+        """This rank's rows of R A P (global coarse columns) and the rows of P for the slab's ghost columns.
+
+        Needed beyond the slab: the rows of A for the fine points of other ranks that my rows of R touch (seam rows
+        interpolate from coarse points across the seam), and the rows of P for every fine column of all those rows.
+        fasp_blas_dcsr_rap assumes square operands (its marker arrays are sized by the row counts,
+        BlaSpmvCSR.c:1042-1050), so the pieces are embedded: fine space = owned + ghost points (rows of A present
+        where needed, empty otherwise), coarse space = owned coarse points + the foreign ones P reaches (empty
+        rows of R)."""
+        comm, rank = self.comm, self.comm.rank
+        c0, c1, k0, k1 = int(off[rank]), int(off[rank + 1]), int(coff[rank]), int(coff[rank + 1])
+        n_loc, nc_loc, NC = c1 - c0, k1 - k0, int(coff[-1])
+        if comm.world == 1:
             A_sq = CSR(n_loc, n_loc, A.ia, A.ja - np.int32(c0), A.val)
-            out = self.F.rap(R_loc, A_sq, P_loc)
-            return CSR(nc_loc, NC, out.ia, out.ja + np.int32(cbase), out.val)
-        ja_e = A.ja - np.int32(c0)
-        outside = np.nonzero((A.ja < c0) | (A.ja >= c1))[0]
-        ja_e[outside] = (n_loc + np.searchsorted(ghosts, A.ja[outside])).astype(np.int32)
-        del outside
-        ia_e = np.concatenate((A.ia, np.full(ng, A.ia[-1], dtype=np.int32)))
-        A_sq = CSR(n_loc + ng, n_loc + ng, ia_e, ja_e, A.val)
-        cg = np.unique(P_gh.ja).astype(np.int64)          # global coarse columns of the ghost rows (not mine)
-        ncg = int(cg.size)
-        pg_ja = (nc_loc + np.searchsorted(cg, P_gh.ja.astype(np.int64))).astype(np.int32)
+            P_sq = CSR(n_loc, nc_loc, P.ia, P.ja - np.int32(k0), P.val)
+            R_sq = CSR(nc_loc, n_loc, R.ia, R.ja - np.int32(c0), R.val)
+            out = self.F.rap(R_sq, A_sq, P_sq)
+            empty = CSR(0, NC, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0))
+            return CSR(nc_loc, NC, out.ia, out.ja + np.int32(k0), out.val), empty
+        GR = np.unique(R.ja[(R.ja < c0) | (R.ja >= c1)]).astype(np.int64)    # foreign fine points in my rows of R
+        A_gr = fetch_rows(comm, A, off, GR)
+        G = np.union1d(np.union1d(ghosts, GR), ghost_columns(A_gr, c0, c1)).astype(np.int64)
+        P_g = fetch_rows(comm, P, off, G)
+        ng = int(G.size)
+
+        def fine_ext(ja):   # global fine column -> index in [owned | G]
+            out = ja - np.int32(c0)
+            outside = np.nonzero((ja < c0) | (ja >= c1))[0]
+            out[outside] = (n_loc + np.searchsorted(G, ja[outside])).astype(np.int32)
+            return out
+
+        cntG = np.zeros(ng, dtype=np.int64)
+        cntG[np.searchsorted(G, GR)] = np.diff(A_gr.ia)
+        ia_e = np.concatenate((A.ia.astype(np.int64), A.ia[-1] + np.cumsum(cntG)))
+        A_sq = CSR(n_loc + ng, n_loc + ng, ia_e.astype(np.int32), np.concatenate((fine_ext(A.ja), fine_ext(A_gr.ja))),
+                   np.concatenate((A.val, A_gr.val)))
+        pj = np.concatenate((P.ja, P_g.ja))
+        foreign = np.nonzero((pj < k0) | (pj >= k1))[0]
+        CG = np.unique(pj[foreign]).astype(np.int64)              # foreign coarse points P reaches
+        ncg = int(CG.size)
+        pj_e = pj - np.int32(k0)
+        pj_e[foreign] = (nc_loc + np.searchsorted(CG, pj[foreign])).astype(np.int32)
         P_sq = CSR(n_loc + ng, nc_loc + ncg,
-                   np.concatenate((P_loc.ia.astype(np.int64), P_loc.ia[-1] + P_gh.ia[1:].astype(np.int64))).astype(np.int32),
-                   np.concatenate((P_loc.ja, pg_ja)), np.concatenate((P_loc.val, P_gh.val)))
-        R_sq = CSR(nc_loc + ncg, n_loc + ng,
-                   np.concatenate((R_loc.ia, np.full(ncg, R_loc.ia[-1], dtype=np.int32))), R_loc.ja, R_loc.val)
+                   np.concatenate((P.ia.astype(np.int64), P.ia[-1] + P_g.ia[1:].astype(np.int64))).astype(np.int32),
+                   pj_e, np.concatenate((P.val, P_g.val)))
+        R_sq = CSR(nc_loc + ncg, n_loc + ng, np.concatenate((R.ia, np.full(ncg, R.ia[-1], dtype=np.int32))),
+                   fine_ext(R.ja), R.val)
         out = self.F.rap(R_sq, A_sq, P_sq)
         nnz = int(out.ia[nc_loc])
         ja = out.ja[:nnz].astype(np.int64)
-        ja_g = np.where(ja < nc_loc, ja + cbase, cg[np.clip(ja - nc_loc, 0, max(ncg - 1, 0))] if ncg else ja)
-        return CSR(nc_loc, NC, out.ia[:nc_loc + 1], ja_g.astype(np.int32), out.val[:nnz])
+        ja_g = ja + k0
+        far = ja >= nc_loc
+        ja_g[far] = CG[ja[far] - nc_loc]
+        A_next = CSR(nc_loc, NC, out.ia[:nc_loc + 1], ja_g.astype(np.int32), out.val[:nnz])
+        # rows of P for the ghost columns of the A slab (the cycle's redundant ghost rows): a subset of P_g
+        sel = np.searchsorted(G, ghosts)
+        cnt = (P_g.ia[sel + 1] - P_g.ia[sel]).astype(np.int64)
+        idx = _ranges(P_g.ia[sel].astype(np.int64), cnt)
+        ia_s = np.zeros(sel.size + 1, dtype=np.int64)
+        np.cumsum(cnt, out=ia_s[1:])
+        return A_next, CSR(sel.size, NC, ia_s.astype(np.int32), P_g.ja[idx], P_g.val[idx])
 
     # -- the solver object --------------------------------------------------------------
     def create_solver(self):

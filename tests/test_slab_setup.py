@@ -75,15 +75,15 @@ WORKER = r'''
 import os, sys, json, ctypes as C
 sys.path.insert(0, %(root)r)
 import numpy as np, torch.distributed as dist
-from faspsolver_b200 import fasp_types as T, problems as PB, slabsetup as SS
+from faspsolver_b200 import fasp_types as T, problems as PB, slabsetup as SS, multigpu as MG
 from oracle.ref import RefFasp
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 comm = SS.HostComm(rank, world)
 ref = RefFasp()
-for name, A in (("p7", PB.poisson7(20)), ("p27", PB.poisson27(16)), ("cd7", PB.convdiff7(14))):
+for name, A, side in (("p7", PB.poisson7(20), 20), ("p27", PB.poisson27(16), 16), ("cd7", PB.convdiff7(14), 14)):
     n = A.shape[0]
-    off = [(n * r) // world for r in range(world + 1)]
+    off = [z * side * side for z in MG.plane_partition(side, world)]      # z-slabs, as the multi-GPU runs cut them
     r0, r1 = off[rank], off[rank + 1]
     As = T.CSR(r1 - r0, n, A.ia[r0:r1 + 1] - A.ia[r0], A.ja[A.ia[r0]:A.ia[r1]], A.val[A.ia[r0]:A.ia[r1]])
     amg = ref.amg_param(print_level=0, smoother=T.SMOOTHER_L1DIAG)
@@ -135,6 +135,41 @@ def test_slab_hierarchy_gloo(tmp_path, world):
     res = [json.loads(l.split("RESULT", 1)[1]) for l in r.stdout.splitlines() if "RESULT" in l]
     assert len(res) == 3
     for d in res:
-        # slab-local coarsening costs a few iterations at the seams (tiny slabs here), never convergence
-        assert 0 < d["st"] <= d["st_ref"] + 3, d
+        # the C/F splitting is slab-local, the interpolation across the seams is not: within two iterations of the
+        # global hierarchy (without seam_interpolation: 17-20 against 11 on the 27-point operator)
+        assert 0 < d["st"] <= d["st_ref"] + 2, d
         assert d["rel"] <= 1e-8 and d["dx"] <= 1e-8, d
+
+
+@pytest.mark.parametrize("gen,n", [(PB.poisson27, 12), (PB.poisson7, 16), (PB.convdiff7, 12)])
+def test_seam_interpolation_restates_fasp_direct_interpolation(ref, gen, n):
+    """The formulas applied to the rows that couple across a seam (strength rule, direct-interpolation weights,
+    truncation) are FASP's own: given the C/F marks of a GLOBAL fasp_amg_coarsening_rs, the rows they produce for a
+    middle slab equal the rows of the global fasp_amg_interp entry for entry (columns, and values to rounding) — on
+    the first level and on a Galerkin coarse level with positive off-diagonal entries."""
+    F = SS._Fasp(ref)
+    A = gen(n)
+    for level in range(2):
+        N = A.shape[0]
+        amg = ref.amg_param(print_level=0, smoother=T.SMOOTHER_L1DIAG)
+        P, vert = F.coarsen_interp(A, amg)                       # FASP's own marks and interpolation, whole matrix
+        cidx = np.nonzero(vert == SS.CGPT)[0]
+        cnum_all = np.full(N, -1, dtype=np.int64)
+        cnum_all[cidx] = np.arange(cidx.size)
+        r0, r1 = N // 3, 2 * N // 3                               # a middle slab: seams on both sides
+        As = T.CSR(r1 - r0, N, A.ia[r0:r1 + 1] - A.ia[r0], A.ja[A.ia[r0]:A.ia[r1]], A.val[A.ia[r0]:A.ia[r1]])
+        ghosts = SS.ghost_columns(As, r0, r1)
+        rows, ia, ja, val = SS.seam_interpolation(As, r0, r1, vert[r0:r1], cnum_all[r0:r1], ghosts, cnum_all[ghosts], amg)
+        assert rows.size > 0
+        for k, i in enumerate(rows):
+            g = i + r0
+            want_j, want_v = P.ja[P.ia[g]:P.ia[g + 1]], P.val[P.ia[g]:P.ia[g + 1]]
+            got_j, got_v = ja[ia[k]:ia[k + 1]], val[ia[k]:ia[k + 1]]
+            assert np.array_equal(got_j, want_j), (level, g)
+            assert np.allclose(got_v, want_v, rtol=1e-13, atol=0), (level, g)
+        # every seam F row of the slab that FASP interpolates is covered
+        seam_f = [i for i in range(r1 - r0) if vert[r0 + i] == SS.FGPT and
+                  ((As.ja[As.ia[i]:As.ia[i + 1]] < r0) | (As.ja[As.ia[i]:As.ia[i + 1]] >= r1)).any() and
+                  P.ia[r0 + i + 1] > P.ia[r0 + i]]
+        assert set(seam_f) <= set(rows.tolist())
+        A = F.rap(F.trans(P), A, P)                               # next level: FASP's own Galerkin operator

@@ -255,4 +255,4 @@ def test_kernel_scheduling_options_do_not_change_results(gpu, ref, data):
             assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2]), name
     finally:
         gpu.fasp_cuda_set_option(b"two_phase_mask", 6.0)
-        gpu.fasp_cuda_set_option(b"vec_u", 4.0)
+        gpu.fasp_cuda_set_option(b"vec_u", 0.0)
