@@ -1,4 +1,5 @@
 #!/usr/bin/env bash
+# (needs the comparison worktrees: git worktree add _ab/<commit> <commit> && build the library in each; _ab/ is git-ignored)
 # A/B on one box: stream priority on/off at HEAD, and the round-1 library (worktree _ab/r01, commit d7c4be1)
 set -u
 cd "$(dirname "$0")/.."

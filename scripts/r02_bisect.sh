@@ -1,4 +1,5 @@
 #!/usr/bin/env bash
+# (needs the comparison worktrees: git worktree add _ab/<commit> <commit> && build the library in each; _ab/ is git-ignored)
 set -u
 cd "$(dirname "$0")/.."
 O=$PWD/gpurun_out/r02bisect

@@ -1,4 +1,5 @@
 #!/usr/bin/env bash
+# (needs the comparison worktrees: git worktree add _ab/<commit> <commit> && build the library in each; _ab/ is git-ignored)
 # why did the L1-sweep kernel get slower in 25d178e with the same SASS? standalone timing + one ncu capture per build
 set -u
 cd "$(dirname "$0")/.."
