@@ -348,3 +348,71 @@ def test_coarse_level_solvers(gpu, ref, data):
     assert st >= 0, (st, api.last_error())
     assert np.all(np.isfinite(xn))
     assert np.linalg.norm(bn - N @ xn) / np.linalg.norm(bn) <= 1e-8 * 1.001
+
+
+def test_remaining_entry_points(gpu, ref, data):
+    """The entry points no other GPU test names: the device-vector cycle, the itsolver driver with the AMG
+    preconditioner object, the relres history, the kernel timer, launch counter, profile dump and sync."""
+    A, b = data["FE"], data["FE_b"]
+    n = A.shape[0]
+    amg = ref.amg_param(print_level=0, smoother=T.SMOOTHER_L1DIAG)
+    mgl = ref.amg_setup(A, amg)
+    try:
+        # z = B r with device vectors equals the host-vector cycle on the same handle
+        h = gpu.fasp_cuda_amg_upload(mgl, C.byref(amg))
+        assert h, gpu.fasp_cuda_last_error()
+        r = np.random.default_rng(8).uniform(-1, 1, n)
+        z_host = np.zeros(n)
+        assert gpu.fasp_cuda_amg_cycle_host(h, T.as_preal(r), T.as_preal(z_host)) == 0
+        d_r, d_z = gpu.fasp_cuda_dvec_alloc(n), gpu.fasp_cuda_dvec_alloc(n)
+        assert gpu.fasp_cuda_dvec_h2d(d_r, T.as_preal(r), n) == 0
+        gpu.fasp_cuda_launch_count_reset()
+        assert gpu.fasp_cuda_amg_cycle_dev(h, d_r, d_z) == 0, gpu.fasp_cuda_last_error()
+        assert gpu.fasp_cuda_sync() == 0
+        assert gpu.fasp_cuda_launch_count() > 0
+        z_dev = np.empty(n)
+        assert gpu.fasp_cuda_dvec_d2h(T.as_preal(z_dev), d_z, n) == 0
+        assert np.array_equal(z_dev, z_host)
+        gpu.fasp_cuda_dvec_free(d_r), gpu.fasp_cuda_dvec_free(d_z)
+        gpu.fasp_cuda_amg_free(h)
+        # fasp_solver_dcsr_itsolver (SolCSR.c:56) with the device preconditioner object, CG and VGMRES
+        pc = gpu.fasp_cuda_precond_from_mgl(mgl, C.byref(amg))
+        assert pc, gpu.fasp_cuda_last_error()
+        for solver in (T.SOLVER_CG, T.SOLVER_VGMRES):
+            it = ref.its_param(itsolver_type=solver, tol=1e-8, maxit=200, print_level=0, restart=30)
+            vb, vx = T.Vec(b), T.Vec(np.zeros(n))
+            st = gpu.fasp_cuda_solver_dcsr_itsolver(A.ptr(), vb.ptr(), vx.ptr(), pc, C.byref(it))
+            amg_r = ref.amg_param(print_level=0, smoother=T.SMOOTHER_L1DIAG)
+            st_ref, x_ref = ref.krylov_amg(A, b, np.zeros(n), it, amg_r)
+            assert st > 0 and abs(st - st_ref) <= 1, (solver, st, st_ref, gpu.fasp_cuda_last_error())
+            assert np.linalg.norm(vx.a - x_ref) / np.linalg.norm(x_ref) <= 1e-8
+        gpu.fasp_cuda_precond_free(pc)
+        # relres history of a resident solver: entry 0 is the initial residual (1 for x0 = 0), the last meets the tolerance
+        s = api.KrylovAmgSolver(mgl, amg)
+        it = ref.its_param(itsolver_type=T.SOLVER_CG, tol=1e-8, maxit=200, print_level=0)
+        st, x = s.solve(b, np.zeros(n), it)
+        hist = s.history()
+        assert st > 0 and hist.size == st + 1 and abs(hist[0] - 1.0) < 1e-12 and hist[-1] <= 1e-8
+        assert s.stat(0) == st and s.stat(3) > 0
+        s.close()
+    finally:
+        ref.amg_free(mgl, amg)
+    # kernel timer and profile records on a resident matrix
+    P7 = PB.poisson7(32)
+    hA = gpu.fasp_cuda_dcsr_upload(P7.ptr())
+    assert hA, gpu.fasp_cuda_last_error()
+    for what in (0, 1, 2, 10, 11):
+        ms = gpu.fasp_cuda_dcsr_time_kernel(hA, what, 1, 3, 0)
+        assert ms > 0, (what, gpu.fasp_cuda_last_error())
+    gpu.fasp_cuda_set_option(b"profile", 1.0)
+    try:
+        gpu.fasp_cuda_profile_dump(None, 0)
+        x = np.ones(P7.shape[1]); y = np.empty(P7.shape[0])
+        assert gpu.fasp_cuda_blas_dcsr_mxv(P7.ptr(), T.as_preal(x), T.as_preal(y)) == 0
+        buf = C.create_string_buffer(1 << 16)
+        gpu.fasp_cuda_profile_dump(buf, len(buf))
+        recs = [ln.split() for ln in buf.value.decode().splitlines()]
+        assert any(int(k) == 0 and int(rows) == P7.shape[0] and int(nnz) == P7.nnz for k, rows, nnz, ms, by in recs)
+    finally:
+        gpu.fasp_cuda_set_option(b"profile", 0.0)
+    gpu.fasp_cuda_dcsr_free(hA)
