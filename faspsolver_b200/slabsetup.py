@@ -21,13 +21,17 @@ The hierarchy is therefore built slab by slab with FASP's OWN per-level routines
        A_{l+1} = R A_l P in global coarse numbering.
   Below `agg_rows` global rows the level is gathered on every rank and FASP's unmodified fasp_amg_setup_rs
   builds the replicated rest of the hierarchy.
+  On a level that one FASP call can hold (max_piece_nnz), steps 1-2 run on neighbouring slabs merged into ONE piece
+  (merged_coarsen_interp: the first rank of a group runs FASP's routines on the group's rows and hands every member
+  its marks and rows of P); the row partition — what the GPUs own — does not change. In practice only the finest
+  level(s) of a system beyond FASP's 32-bit limit are split slab by slab; below them the hierarchy is FASP's global one.
 
 With ONE rank every step degenerates to the reference's own call sequence on the same data, so the hierarchy
 is bit-identical to fasp_amg_setup_rs (tests/test_slab_setup.py). With several ranks the C/F splitting near the
 seams differs from the global one (slab-local, as in hypre's "RS0"); the hierarchy is still a Galerkin hierarchy
 of the true operator. Iterations of the reference's CPU PCG on the assembled hierarchy, 27-point operator:
 48^3 / 64^3 on 4 slabs 11 / 12 (global hierarchy 11; without step 2b: 20 / 23), 96^3 on 2 slabs 12 (12; 24),
-128^3 on 2 slabs 18 (13; 30). Its oracle: the slabs are assembled into global CSR matrices (small
+128^3 on 2 slabs 18 (13; 30); with the levels that fit one piece merged: the global count. Its oracle: the slabs are assembled into global CSR matrices (small
 sizes) and handed to the REFERENCE's fasp_solver_dcsr_pcg + fasp_precond_amg (`assemble_global`).
 
 Host-side plumbing (torch.distributed, gloo) moves index lists and matrix rows between the ranks at setup;
@@ -66,36 +70,39 @@ class HostComm:
         dist.all_gather_object(out, obj)
         return out
 
+    CHUNK = 1 << 28   # bytes per message: large slabs travel in pieces (a merged level can be several GB)
+
     def alltoall(self, items):
         """items[q] goes to rank q; returns what every rank sent to me (by source rank)."""
         if self.world == 1:
             return [items[0]]
         import torch
         import torch.distributed as dist
-        blobs = [pickle.dumps(it, protocol=pickle.HIGHEST_PROTOCOL) if q != self.rank else b""
+        blobs = [pickle.dumps(it, protocol=pickle.HIGHEST_PROTOCOL) if (q != self.rank and it is not None) else b""
                  for q, it in enumerate(items)]
         sizes = self.allgather([len(b) for b in blobs])
-        reqs, recv, keep = [], {}, []
-        for q in range(self.world):
-            if q == self.rank:
-                continue
-            n_in = sizes[q][self.rank]
-            if n_in:
-                t = torch.empty(n_in, dtype=torch.uint8)
-                recv[q] = t
-                reqs.append(dist.irecv(t, src=q))
-            if len(blobs[q]):
-                t = torch.frombuffer(bytearray(blobs[q]), dtype=torch.uint8)
-                keep.append(t)
-                reqs.append(dist.isend(t, dst=q))
-        for r in reqs:
-            r.wait()
+        recv = {q: torch.empty(sizes[q][self.rank], dtype=torch.uint8)
+                for q in range(self.world) if q != self.rank and sizes[q][self.rank]}
+        send = {q: torch.frombuffer(memoryview(blobs[q]), dtype=torch.uint8) for q in range(self.world) if len(blobs[q])}
+        rounds = max([0] + [(t.numel() + self.CHUNK - 1) // self.CHUNK for t in list(recv.values()) + list(send.values())])
+        rounds = max(self.allgather(int(rounds)))
+        for k in range(rounds):
+            lo, hi = k * self.CHUNK, (k + 1) * self.CHUNK
+            reqs = []
+            for q, t in recv.items():
+                if lo < t.numel():
+                    reqs.append(dist.irecv(t[lo:min(hi, t.numel())], src=q))
+            for q, t in send.items():
+                if lo < t.numel():
+                    reqs.append(dist.isend(t[lo:min(hi, t.numel())], dst=q))
+            for r in reqs:
+                r.wait()
         out = []
         for q in range(self.world):
             if q == self.rank:
                 out.append(items[q])
             else:
-                out.append(pickle.loads(recv[q].numpy().tobytes()) if q in recv else None)
+                out.append(pickle.loads(memoryview(recv[q].numpy())) if q in recv else None)
         return out
 
 
@@ -240,7 +247,7 @@ def fetch_ints(comm: HostComm, x_loc, off, want):
     return fetch_entries(comm, np.asarray(x_loc, dtype=np.float64), off, want).astype(np.int64)
 
 
-def seam_interpolation(A: CSR, c0, c1, vert, cnum, ghosts, ghost_cnum, amg):
+def seam_interpolation(A: CSR, c0, c1, vert, cnum, ghosts, ghost_cnum, amg, group=None):
     """Interpolation rows of the F points that couple across a seam, from their FULL rows of A.
 
     The slab-local rows FASP computed for them use only the coarse points of their own side — a one-sided formula
@@ -254,7 +261,8 @@ def seam_interpolation(A: CSR, c0, c1, vert, cnum, ghosts, ghost_cnum, amg):
     cnum[i]: global coarse number of owned point i or -1; ghost_cnum likewise for `ghosts`.
     Returns (rows, ia, ja, val): new P rows (global coarse columns) for the seam F rows that have a pattern."""
     n = A.shape[0]
-    out_idx = np.nonzero((A.ja < c0) | (A.ja >= c1))[0]
+    g0, g1 = group if group is not None else (c0, c1)   # the range FASP's splitting saw as one piece (merged slabs)
+    out_idx = np.nonzero((A.ja < g0) | (A.ja >= g1))[0]
     seam = np.unique(np.searchsorted(A.ia, out_idx, side="right") - 1)
     seam = seam[vert[seam] != CGPT]     # F points and the points FASP found isolated inside the slab (ISPT)
     if seam.size == 0:
@@ -314,6 +322,65 @@ def seam_interpolation(A: CSR, c0, c1, vert, cnum, ghosts, ghost_cnum, amg):
     ia = np.zeros(rows_out.size + 1, dtype=np.int64)
     np.cumsum(cnt_out, out=ia[1:])
     return seam[rows_out], ia, kc.astype(np.int32), kw      # entries are already grouped by row (ascending)
+
+
+def merge_factor(comm: HostComm, A: CSR, max_piece_nnz):
+    """How many neighbouring slabs FASP's splitting sees as ONE piece on this level: as many as one piece can hold
+    (a power of two; max_piece_nnz nonzeros — below the 2^31 of FASP's INT, ~60 bytes of host memory each on the rank
+    that runs it). Slab-local splitting is exact on a regular fine grid (the 27-point level 0 comes out entry for
+    entry as the global one), but seams on the irregular coarser levels cost convergence, and erratically so —
+    27-pt 128^3, iterations of the reference's PCG on the assembled hierarchy: global 13; two pieces on every level
+    18; two pieces on levels 0-2 only 13, on levels 0-1 only 16; four pieces on level 0, two on level 2, one
+    elsewhere 24. The coarser levels are a fraction of the finest and mostly fit one piece, so the seams stay on the
+    level(s) no single dCSRmat could hold and below them the hierarchy is FASP's global one. Collective."""
+    world = comm.world
+    nnz = np.array(comm.allgather(int(A.nnz)), dtype=np.int64)
+    g = 1
+    while g < world:
+        g2 = g * 2
+        sums = [int(nnz[k:k + g2].sum()) for k in range(0, world, g2)]
+        if max(sums) > max_piece_nnz:
+            break
+        g = g2
+    return min(g, world) if g < world else world
+
+
+def merged_coarsen_interp(comm: HostComm, F: "_Fasp", A: CSR, off, g, amg):
+    """fasp_amg_coarsening_rs + fasp_amg_interp on g neighbouring slabs as one piece: the first rank of every group
+    fetches the group's rows, runs FASP's routines on them and hands every member the C/F marks and the rows of P
+    of its own points (columns = coarse numbers inside the group, ascending in the fine index). The ROW partition of
+    the level is untouched: only the setup of this level is agglomerated. Returns (P_rows, vert) or None. Collective."""
+    world, rank = comm.world, comm.rank
+    lead = (rank // g) * g
+    last = min(lead + g, world)
+    c0, c1 = int(off[rank]), int(off[rank + 1])
+    g0, g1 = int(off[lead]), int(off[last])
+    want = np.arange(c1, g1, dtype=np.int64) if rank == lead else np.zeros(0, dtype=np.int64)
+    rest = fetch_rows(comm, A, off, want)
+    send = [None] * world
+    mine = None
+    if rank == lead:
+        A_M = _stack_rows(A, rest)
+        got = F.coarsen_interp(local_block(A_M, g0, g1), amg) if A_M.shape[0] > 0 else None
+        for q in range(lead, last):
+            if got is None:
+                piece = "failed"
+            else:
+                P_M, vert_M = got
+                r0, r1 = int(off[q]) - g0, int(off[q + 1]) - g0
+                e0, e1 = int(P_M.ia[r0]), int(P_M.ia[r1])
+                piece = (P_M.ia[r0:r1 + 1] - P_M.ia[r0], P_M.ja[e0:e1], P_M.val[e0:e1], vert_M[r0:r1], P_M.shape[1])
+            if q == rank:
+                mine = piece
+            else:
+                send[q] = piece
+    got_all = comm.alltoall(send)
+    if rank != lead:
+        mine = got_all[lead]
+    if mine is None or isinstance(mine, str):
+        return None
+    ia, ja, val, vert, ncg = mine
+    return CSR(c1 - c0, int(ncg), ia, ja, val), np.asarray(vert)
 
 
 def replace_rows(P: CSR, rows, ia_new, ja_new, val_new):
@@ -401,7 +468,7 @@ class SlabLevel:
 
 class SlabHierarchy:
     def __init__(self, hf, A_slab: CSR, off, amg, comm: HostComm | None = None, agg_rows=8000, log=None,
-                 seam_interp=True):
+                 seam_interp=True, max_piece_nnz=600_000_000):
         self.hf, self.amg = hf, amg
         self.comm = comm or HostComm()
         self.F = _Fasp(hf)
@@ -420,8 +487,14 @@ class SlabHierarchy:
             c0, c1 = int(off[rank]), int(off[rank + 1])
             n_loc = c1 - c0
             assert A.shape[0] == n_loc
-            got = self.F.coarsen_interp(local_block(A, c0, c1), amg) if n_loc > 0 else None
-            info = comm.allgather((got is not None or n_loc == 0, 0 if got is None else got[0].shape[1]))
+            g = merge_factor(comm, A, max_piece_nnz) if (comm.world > 1 and seam_interp) else 1
+            lead = (rank // g) * g
+            grp = (int(off[lead]), int(off[min(lead + g, comm.world)]))
+            if g > 1:
+                got = merged_coarsen_interp(comm, self.F, A, off, g, amg)
+            else:
+                got = self.F.coarsen_interp(local_block(A, c0, c1), amg) if n_loc > 0 else None
+            info = comm.allgather((got is not None or n_loc == 0, 0 if got is None else int((got[1] == CGPT).sum())))
             if not all(ok for ok, _ in info):
                 break
             ncs = np.array([nc for _, nc in info], dtype=np.int64)
@@ -433,8 +506,9 @@ class SlabHierarchy:
                 P_loc, vert = CSR(0, 0, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0)), np.zeros(0, np.int32)
             else:
                 P_loc, vert = got
-            nc_loc = P_loc.shape[1]
-            P_glob = CSR(n_loc, NC, P_loc.ia, P_loc.ja + np.int32(coff[rank]), P_loc.val)
+            nc_loc = int(coff[rank + 1] - coff[rank])
+            # columns of P_loc count the coarse points of the piece FASP saw: the slab, or the merged group
+            P_glob = CSR(n_loc, NC, P_loc.ia, P_loc.ja + np.int32(coff[lead]), P_loc.val)
             ghosts = ghost_columns(A, c0, c1)
             n_seam = 0
             if comm.world > 1 and seam_interp:
@@ -444,7 +518,7 @@ class SlabHierarchy:
                 cidx = np.nonzero(vert == CGPT)[0]
                 cnum[cidx] = int(coff[rank]) + np.arange(cidx.size)
                 ghost_cnum = fetch_ints(comm, cnum, off, ghosts)
-                rows, ia_n, ja_n, val_n = seam_interpolation(A, c0, c1, vert, cnum, ghosts, ghost_cnum, amg)
+                rows, ia_n, ja_n, val_n = seam_interpolation(A, c0, c1, vert, cnum, ghosts, ghost_cnum, amg, group=grp)
                 P_glob = replace_rows(P_glob, rows, ia_n, ja_n, val_n)
                 n_seam = int(rows.size)
             if comm.world > 1:
@@ -460,8 +534,8 @@ class SlabHierarchy:
             lv.R = R_glob
             lv.n_rext = 0
             self.levels.append(lv)
-            log("[slab setup] level %d: %d rows (%d here, %d ghosts, %d seam rows re-interpolated) -> %d coarse rows" %
-                (len(self.levels) - 1, int(off[-1]), n_loc, ghosts.size, n_seam, NC))
+            log("[slab setup] level %d: %d rows (%d here, %d ghosts, split in pieces of %d slab(s), %d seam rows "
+                "re-interpolated) -> %d coarse rows" % (len(self.levels) - 1, int(off[-1]), n_loc, ghosts.size, g, n_seam, NC))
             A, off = A_next, coff
         if not self.levels:
             raise ValueError("slab setup: the finest level could not be coarsened on every rank")

@@ -32,6 +32,8 @@ def parse(argv=None):
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--agg-rows", type=int, default=8000)
+    ap.add_argument("--max-piece-nnz", type=float, default=6e8,
+                    help="levels up to this many nonzeros are split by FASP as one piece (0: always slab by slab)")
     ap.add_argument("--opt", action="append", default=[])
     ap.add_argument("--profile", type=int, default=1)
     ap.add_argument("--lock", default="", help="one GPU shared with other bench processes: lock file around the GPU phase")
@@ -58,7 +60,7 @@ def run(args, own_comm=True):
     # matrix, the embedded Galerkin operands); refuse to start rather than drive the box out of memory
     import psutil
     nnz_est = float(args.stencil) * (zoff[rank + 1] - zoff[rank]) * n * n
-    need_all = 60.0 * nnz_est * world
+    need_all = 60.0 * nnz_est * world + 60.0 * min(nnz_est * world, args.max_piece_nnz)   # + the rank that runs a merged piece
     avail = psutil.virtual_memory().available
     log("[config3] host memory: about %.0f GB needed by %d ranks, %.0f GB available" % (need_all / 1e9, world, avail / 1e9))
     if need_all > 0.9 * avail:
@@ -75,7 +77,7 @@ def run(args, own_comm=True):
     amg, it = B.amg_recipe(hf)
     comm = SS.HostComm(rank, world)
     t = time.time()
-    sh = SS.SlabHierarchy(hf, A, off, amg, comm, agg_rows=args.agg_rows, log=log)
+    sh = SS.SlabHierarchy(hf, A, off, amg, comm, agg_rows=args.agg_rows, log=log, max_piece_nnz=int(args.max_piece_nnz))
     t_setup = time.time() - t
     lock_f = None
     if args.lock:

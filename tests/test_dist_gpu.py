@@ -96,7 +96,9 @@ for name, gen, n, smoother in (("p27", PB.poisson27, 24, T.SMOOTHER_L1DIAG), ("p
     relax = 0.67 if smoother == T.SMOOTHER_JACOBI else 1.0
     amg = ref.amg_param(print_level=0, smoother=smoother, relaxation=relax)
     it = ref.its_param(itsolver_type=T.SOLVER_CG, tol=1e-8, maxit=200, print_level=0)
-    sh = SS.SlabHierarchy(ref, As, off, amg, comm, agg_rows=1500)
+    # p27: slab by slab on every level (seam rows re-interpolated, P and R with foreign columns); p7: the default,
+    # levels that fit one FASP call are split as one piece
+    sh = SS.SlabHierarchy(ref, As, off, amg, comm, agg_rows=1500, **({"max_piece_nnz": 0} if name == "p27" else {}))
     assert len(sh.levels) >= 2
     nloc = As.shape[0]
     b_loc = np.ones(nloc)

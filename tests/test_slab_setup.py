@@ -79,6 +79,7 @@ from faspsolver_b200 import fasp_types as T, problems as PB, slabsetup as SS, mu
 from oracle.ref import RefFasp
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
+SS.HostComm.CHUNK = 1 << 12          # every exchange in many small messages: the chunked all-to-all is on the path
 comm = SS.HostComm(rank, world)
 ref = RefFasp()
 for name, A, side in (("p7", PB.poisson7(20), 20), ("p27", PB.poisson27(16), 16), ("cd7", PB.convdiff7(14), 14)):
@@ -87,7 +88,9 @@ for name, A, side in (("p7", PB.poisson7(20), 20), ("p27", PB.poisson27(16), 16)
     r0, r1 = off[rank], off[rank + 1]
     As = T.CSR(r1 - r0, n, A.ia[r0:r1 + 1] - A.ia[r0], A.ja[A.ia[r0]:A.ia[r1]], A.val[A.ia[r0]:A.ia[r1]])
     amg = ref.amg_param(print_level=0, smoother=T.SMOOTHER_L1DIAG)
-    sh = SS.SlabHierarchy(ref, As, off, amg, comm, agg_rows=300)
+    # p7 / cd7: every level slab by slab (max_piece_nnz = 0: nothing is merged); p27: levels above 60 k nonzeros slab
+    # by slab, the smaller ones merged into one piece (FASP's routines run once, on the first rank)
+    sh = SS.SlabHierarchy(ref, As, off, amg, comm, agg_rows=300, max_piece_nnz=60000 if name == "p27" else 0)
     glob, tailA = sh.assemble_global()
     for l, (Al, Pl, Rl) in enumerate(glob):
         a, p, r = Al.to_scipy(), Pl.to_scipy(), Rl.to_scipy()
