@@ -338,8 +338,8 @@ def merge_factor(comm: HostComm, A: CSR, max_piece_nnz):
     g = 1
     while g < world:
         g2 = g * 2
-        sums = [int(nnz[k:k + g2].sum()) for k in range(0, world, g2)]
-        if max(sums) > max_piece_nnz:
+        sums = [int(nnz[k:k + g2].sum()) for k in range(0, world, g2) if min(k + g2, world) - k > 1]
+        if sums and max(sums) > max_piece_nnz:   # (a lone slab is a piece whatever its size)
             break
         g = g2
     return min(g, world) if g < world else world

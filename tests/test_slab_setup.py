@@ -176,3 +176,22 @@ def test_seam_interpolation_restates_fasp_direct_interpolation(ref, gen, n):
                   P.ia[r0 + i + 1] > P.ia[r0 + i]]
         assert set(seam_f) <= set(rows.tolist())
         A = F.rap(F.trans(P), A, P)                               # next level: FASP's own Galerkin operator
+
+
+def test_merge_factor_rule():
+    """Pieces are the largest power-of-two groups of neighbouring slabs whose nonzeros fit one FASP call."""
+    class FakeComm(SS.HostComm):
+        def __init__(self, rank, nnz):
+            super().__init__(rank, len(nnz))
+            self._nnz = nnz
+        def allgather(self, obj):
+            return list(self._nnz)
+    A = T.CSR(1, 1, [0, 1], [0], [1.0])
+    eq = [100] * 8
+    assert SS.merge_factor(FakeComm(0, eq), A, 0) == 1               # nothing fits: slab by slab
+    assert SS.merge_factor(FakeComm(3, eq), A, 199) == 1
+    assert SS.merge_factor(FakeComm(3, eq), A, 200) == 2
+    assert SS.merge_factor(FakeComm(3, eq), A, 799) == 4
+    assert SS.merge_factor(FakeComm(3, eq), A, 800) == 8             # the whole chain: FASP's global splitting
+    assert SS.merge_factor(FakeComm(1, [100, 100, 500]), A, 250) == 2   # 3 ranks: groups [0,1] and [2] (500 > 250 alone is
+    assert SS.merge_factor(FakeComm(1, [100, 100, 100]), A, 1000) == 3  # allowed: a single slab is never split further)
